@@ -1,0 +1,130 @@
+/*
+ * vlmerge.h — C ABI of libvlmerge.so, the B200 (sm_100a) merge hot path of ylsung/vl-merging.
+ *
+ * The reference has no FFI layer: its operator boundary is (1) a PyTorch forward hook and
+ * (2) three state_dict -> state_dict methods.  Each entry point below replaces
+ * the arithmetic of one reference call site; the Python shim in vl-merging_b200/ binds them with
+ * ctypes and mirrors the reference's hook / merge-method signatures on top.
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, <0 = vlm_status, >0 = cudaError_t.  Nothing throws.
+ *     vlm_last_error() returns a thread-local message for the last non-zero return.
+ *   - all pointers are DEVICE pointers unless the name ends in _host.  The library borrows them
+ *     for the duration of the call (work is enqueued on `stream`, a cudaStream_t passed as void*;
+ *     NULL = legacy default stream) and never frees or retains them.
+ *   - matrices are row-major with leading dimension in ELEMENTS.
+ *   - there is no CPU path: without a CUDA device every compute entry point fails.
+ */
+#ifndef VLMERGE_H_
+#define VLMERGE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLM_ABI_VERSION 1
+
+typedef enum {
+  VLM_OK = 0,
+  VLM_ERR_INVALID_ARG = -1,   /* null pointer, negative size, bad enum */
+  VLM_ERR_ALIGNMENT = -2,     /* pointer / leading dimension not usable by the requested path */
+  VLM_ERR_UNSUPPORTED = -3,   /* e.g. device is not sm_100 */
+  VLM_ERR_DRIVER = -4,        /* cuTensorMapEncodeTiled / cuSOLVER symbol lookup failed */
+  VLM_ERR_NOT_SPD = -5,       /* Cholesky failed: summed Gram is singular / not positive definite */
+  VLM_ERR_INTERNAL = -6
+} vlm_status;
+
+typedef enum { VLM_F32 = 0, VLM_BF16 = 1, VLM_F16 = 2, VLM_F64 = 3 } vlm_dtype;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int         vlm_version(void);          /* VLM_ABI_VERSION */
+const char* vlm_last_error(void);       /* thread-local, never NULL */
+/* number of kernels this library has launched in the calling process (bench.py gpu_launches) */
+uint64_t    vlm_launch_count(void);
+
+/* ---- (a) Gram accumulation -----------------------------------------------------------------
+ * Replaces hook_gram_input, src/cache_gram_matrices.py:246-254:
+ *     flatten_input = input.reshape(-1, D).to(float64); gram = flatten_input.T @ flatten_input
+ *     middle_representations[name] += gram.cpu()
+ * G[r][c] += sum_k X[k][r] * X[k][c]  for every c >= r (upper triangle; elements below the
+ * diagonal are scratch until vlm_sym_finalize).  X is the hooked activation viewed as
+ * [rows, d] (f32 -> TF32 tensor cores, bf16/f16 -> f16-kind tensor cores), accumulation is fp32
+ * in TMEM and fp32 in G.  Requires x 16-byte aligned and ldx*sizeof(elem) % 16 == 0, g 16-byte
+ * aligned and ldg % 4 == 0; otherwise VLM_ERR_ALIGNMENT (use vlm_syrk_accum_simt).
+ * rows == 0 is a no-op. */
+int vlm_syrk_accum(const void* x, int dtype, int64_t rows, int d, int64_t ldx,
+                   float* g, int64_t ldg, void* stream);
+
+/* Same contract on CUDA cores (fp32 FMA), any alignment.  Debug oracle on the device and the
+ * path for activations TMA cannot address. */
+int vlm_syrk_accum_simt(const void* x, int dtype, int64_t rows, int d, int64_t ldx,
+                        float* g, int64_t ldg, void* stream);
+
+/* Mirror the upper triangle into the lower one (G[c][r] = G[r][c], c > r) and, if out_f64 is not
+ * NULL, also write the full symmetric matrix widened to fp64 — the dtype of the reference's Gram
+ * file (src/cache_gram_matrices.py:251,349). */
+int vlm_sym_finalize(float* g, int d, int64_t ldg, double* out_f64, int64_t ld64, void* stream);
+
+/* Host-only view of vlm_syrk_accum's work decomposition for (rows, d) on a device with nsm SMs
+ * (elem_bytes 4 = f32, 2 = bf16/f16): writes segments as 5 int32 each {row_block_col0, col_block_col0,
+ * width_in_128_blocks, chunk_begin, chunk_end} and ncta+1 offsets into them.  Returns the number of
+ * segments (>= 0) or a vlm_status.  No CUDA calls; used by the CPU tests. */
+int vlm_syrk_schedule_host(int64_t rows, int d, int elem_bytes, int nsm, int32_t* segs_out, int cap,
+                           int32_t* off_out, int off_cap, int* ncta_out);
+
+/* ---- (b) streaming merge -------------------------------------------------------------------
+ * Replaces the per-tensor loops of merge_weights (src/vilt/modules/vilt_module.py:586-635),
+ * sum_task_vectors (:696-744) and the simple-average branches of regmean (:436-457, :486-529).
+ * One launch streams every segment once; fp32, rounding order identical to the reference:
+ *   VLM_MERGE_WSUM     dst = (c0*s0) + (c1*s1) + ...            (products rounded, then added)
+ *   VLM_MERGE_SEQ_LERP dst = s0; dst = dst + c_m*(s_m - dst)    m = 1..n_src-1  (s0 = central;
+ *                      the reference's aliased in-place update)
+ *   VLM_MERGE_MEAN     dst = (s0 + s1 + ...) / n_src
+ */
+typedef enum { VLM_MERGE_WSUM = 0, VLM_MERGE_SEQ_LERP = 1, VLM_MERGE_MEAN = 2 } vlm_merge_mode;
+#define VLM_MERGE_MAX_SRC 4
+
+typedef struct {
+  float*       dst;                       /* n fp32 elements (device) */
+  const float* src[VLM_MERGE_MAX_SRC];    /* n_src device pointers, n elements each */
+  float        coef[VLM_MERGE_MAX_SRC];   /* per-source coefficient (unused for MEAN; coef[0] unused for SEQ_LERP) */
+  uint64_t     n;
+  int32_t      n_src;                     /* 1..VLM_MERGE_MAX_SRC */
+  int32_t      mode;                      /* vlm_merge_mode */
+} vlm_merge_seg;
+
+typedef struct vlm_merge_plan vlm_merge_plan;
+/* Upload the segment table once (host array), run it any number of times. */
+int vlm_merge_plan_create(const vlm_merge_seg* segs_host, int n_seg, vlm_merge_plan** out);
+int vlm_merge_plan_run(const vlm_merge_plan* plan, void* stream);
+int vlm_merge_plan_destroy(vlm_merge_plan* plan);
+/* algorithmic bytes one run moves: sum over segments of (n_src + 1) * n * 4 */
+uint64_t vlm_merge_plan_bytes(const vlm_merge_plan* plan);
+
+/* ---- (c) RegMean ---------------------------------------------------------------------------
+ * Replaces, in regmean (src/vilt/modules/vilt_module.py:366-531):
+ *   scale_G (:388-392)              Ghat = a*G + (1-a)*diag(G)
+ *   summed_gram += G (:423,474)     vlm_gram_scale_accum
+ *   later_weight += W.double() @ G (:424,475)   vlm_regmean_rhs
+ *   matmul(later_weight, inverse(summed_gram)) (:432-434,:483-484)   vlm_spd_solve_right
+ * All fp64 like the reference.  g_dtype is VLM_F64 (the reference's Gram file) or VLM_F32 (our
+ * on-device Gram buffers); G must be the full symmetric matrix (after vlm_sym_finalize). */
+int vlm_gram_scale_accum(const void* g, int g_dtype, int d, int64_t ldg, double alpha,
+                         double* out, int64_t ldo, int accumulate, void* stream);
+/* acc[out_f][in_f] (+)= sum_k W[out_f][k] * Ghat[k][in_f];  W fp32 (out_f x in_f), G (in_f x in_f). */
+int vlm_regmean_rhs(const float* w, int out_f, int in_f, int64_t ldw,
+                    const void* g, int g_dtype, int64_t ldg, double alpha,
+                    double* acc, int64_t ldacc, int accumulate, void* stream);
+/* X = R * S^{-1} for SPD S (in_f x in_f, fp64, overwritten by its Cholesky factor); R (out_f x
+ * in_f, fp64) is overwritten by X.  cuSOLVER potrf/potrs; off the hot path, timed separately.
+ * Synchronises `stream` to read the factorisation status. */
+int vlm_spd_solve_right(double* s, int in_f, int64_t lds, double* r, int out_f, int64_t ldr,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLMERGE_H_ */

@@ -1,0 +1,120 @@
+// api.cu — C-ABI entry points declared in include/vlmerge.h (argument validation, error state) for
+// the Gram path; merge.cu and regmean.cu define their own entry points.
+#include <cstdarg>
+#include <mutex>
+
+#include "common.cuh"
+#include "syrk.h"
+
+namespace vlm {
+
+std::atomic<uint64_t> g_launches{0};
+
+std::string& last_error_ref() {
+  static thread_local std::string msg;
+  return msg;
+}
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error_ref() = buf;
+  return code;
+}
+
+namespace {
+std::mutex g_dev_mu;
+int g_sm_count[64] = {};
+int g_cc_major[64] = {};
+}  // namespace
+
+int device_sm_count(int* out) {
+  int dev = 0;
+  VLM_CUDA(cudaGetDevice(&dev));
+  VLM_REQUIRE(dev >= 0 && dev < 64, VLM_ERR_UNSUPPORTED, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (g_sm_count[dev] == 0) {
+    VLM_CUDA(cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+    VLM_CUDA(cudaDeviceGetAttribute(&g_cc_major[dev], cudaDevAttrComputeCapabilityMajor, dev));
+  }
+  *out = g_sm_count[dev];
+  return 0;
+}
+
+int require_sm100() {
+  int nsm = 0, dev = 0;
+  if (int rc = device_sm_count(&nsm)) return rc;
+  VLM_CUDA(cudaGetDevice(&dev));
+  VLM_REQUIRE(g_cc_major[dev] == 10, VLM_ERR_UNSUPPORTED,
+              "libvlmerge is built for sm_100a only (device compute capability major = %d)", g_cc_major[dev]);
+  return 0;
+}
+
+namespace {
+int check_syrk_args(const char* who, const void* x, int dtype, int64_t rows, int d, int64_t ldx, const float* g,
+                    int64_t ldg) {
+  VLM_REQUIRE(dtype == VLM_F32 || dtype == VLM_BF16 || dtype == VLM_F16, VLM_ERR_INVALID_ARG,
+              "%s: dtype must be VLM_F32, VLM_BF16 or VLM_F16 (got %d)", who, dtype);
+  VLM_REQUIRE(rows >= 0 && d > 0, VLM_ERR_INVALID_ARG, "%s: rows=%lld d=%d", who, (long long)rows, d);
+  VLM_REQUIRE(g != nullptr && ldg >= d, VLM_ERR_INVALID_ARG, "%s: g is NULL or ldg < d", who);
+  VLM_REQUIRE(rows == 0 || (x != nullptr && ldx >= d), VLM_ERR_INVALID_ARG, "%s: x is NULL or ldx < d", who);
+  return 0;
+}
+}  // namespace
+
+}  // namespace vlm
+
+using namespace vlm;
+
+extern "C" int vlm_version(void) { return VLM_ABI_VERSION; }
+extern "C" const char* vlm_last_error(void) { return last_error_ref().c_str(); }
+extern "C" uint64_t vlm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int vlm_syrk_accum(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,
+                              void* stream) {
+  if (int rc = check_syrk_args("vlm_syrk_accum", x, dtype, rows, d, ldx, g, ldg)) return rc;
+  if (rows == 0) return 0;
+  if (int rc = require_sm100()) return rc;
+  return syrk_tc_launch(x, dtype, rows, d, ldx, g, ldg, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vlm_syrk_accum_simt(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,
+                                   void* stream) {
+  if (int rc = check_syrk_args("vlm_syrk_accum_simt", x, dtype, rows, d, ldx, g, ldg)) return rc;
+  if (rows == 0) return 0;
+  return syrk_simt_launch(x, dtype, rows, d, ldx, g, ldg, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vlm_sym_finalize(float* g, int d, int64_t ldg, double* out_f64, int64_t ld64, void* stream) {
+  VLM_REQUIRE(g != nullptr && d > 0 && ldg >= d, VLM_ERR_INVALID_ARG, "vlm_sym_finalize: bad arguments");
+  VLM_REQUIRE(out_f64 == nullptr || ld64 >= d, VLM_ERR_INVALID_ARG, "vlm_sym_finalize: ld64 < d");
+  return sym_finalize_launch(g, d, ldg, out_f64, ld64, static_cast<cudaStream_t>(stream));
+}
+
+// Host-only view of the SYRK work decomposition (tests/test_schedule.py): fills up to cap segments
+// as 5 ints each {col_a, col_b, w, k0, k1} and ncta+1 offsets; returns the number of segments or
+// a negative vlm_status.
+extern "C" int vlm_syrk_schedule_host(int64_t rows, int d, int elem_bytes, int nsm, int32_t* segs_out, int cap,
+                                      int32_t* off_out, int off_cap, int* ncta_out) {
+  VLM_REQUIRE(rows > 0 && d > 0 && (elem_bytes == 2 || elem_bytes == 4) && nsm > 0 && ncta_out, VLM_ERR_INVALID_ARG,
+              "vlm_syrk_schedule_host: bad arguments");
+  const int bk = 128 / elem_bytes;
+  std::vector<SyrkSeg> segs;
+  std::vector<int> off;
+  build_syrk_schedule((rows + bk - 1) / bk, d, nsm, &segs, &off);
+  *ncta_out = (int)off.size() - 1;
+  VLM_REQUIRE((int)segs.size() <= cap && (int)off.size() <= off_cap, VLM_ERR_INVALID_ARG,
+              "vlm_syrk_schedule_host: output capacity too small (%d segments)", (int)segs.size());
+  for (size_t i = 0; i < segs.size(); ++i) {
+    segs_out[5 * i + 0] = segs[i].col_a;
+    segs_out[5 * i + 1] = segs[i].col_b;
+    segs_out[5 * i + 2] = segs[i].w;
+    segs_out[5 * i + 3] = segs[i].k0;
+    segs_out[5 * i + 4] = segs[i].k1;
+  }
+  for (size_t i = 0; i < off.size(); ++i) off_out[i] = off[i];
+  return (int)segs.size();
+}

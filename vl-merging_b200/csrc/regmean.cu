@@ -1,0 +1,228 @@
+// regmean.cu — kernel (c): the RegMean right-hand side  acc (+)= W * Ghat  and the summed, scaled
+// Gram, both fp64 like the reference (src/vilt/modules/vilt_module.py:388-392 scale_G, :423-424 and
+// :474-475 `summed_gram += G; later_weight += W.double() @ G`), plus the SPD solve that replaces
+// `matmul(later_weight, torch.inverse(summed_gram))` (:432-434, :483-484) through cuSOLVER.
+//
+// The GEMM runs on the fp64 tensor-core path (mma.sync m8n8k4 DMMA): RegMean multiplies by the
+// inverse of an ill-conditioned Gram sum afterwards, so the right-hand side keeps the reference's
+// precision instead of a split-TF32 approximation.  scale_G is fused into the operand load:
+// Ghat[k][n] = alpha*G[k][n] off the diagonal and alpha*g + (1-alpha)*g on it (the reference's own
+// rounding), so the scaled Gram is never materialised.
+#include <dlfcn.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace vlm {
+namespace {
+
+__device__ __forceinline__ double scaled_g(double g, bool on_diag, double alpha, double one_minus_alpha) {
+  const double a = __dmul_rn(alpha, g);
+  return on_diag ? __dadd_rn(a, __dmul_rn(one_minus_alpha, g)) : a;
+}
+
+template <typename GT>
+__global__ void __launch_bounds__(256)
+gram_scale_accum_kernel(const GT* __restrict__ g, int d, int64_t ldg, double alpha, double oma,
+                        double* __restrict__ out, int64_t ldo, int accumulate) {
+  const int64_t n = (int64_t)d * d;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / d), c = (int)(e % d);
+    const double v = scaled_g((double)g[(int64_t)r * ldg + c], r == c, alpha, oma);
+    double* o = out + (int64_t)r * ldo + c;
+    *o = accumulate ? __dadd_rn(*o, v) : v;
+  }
+}
+
+// acc[M x N] (+)= W[M x K] * Ghat[K x N], K == N == in_f.  Block tile 64x64, K step 16, 4 warps
+// (2x2), each warp 32x32 = 4x4 m8n8k4 tiles.
+constexpr int BM = 64, BN = 64, BKK = 16;
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <typename GT>
+__global__ void __launch_bounds__(128)
+regmean_rhs_kernel(const float* __restrict__ w, int M, int K, int64_t ldw, const GT* __restrict__ g, int64_t ldg,
+                   double alpha, double oma, double* __restrict__ acc, int64_t ldacc, int accumulate) {
+  __shared__ double sa[2][BM][BKK + 1];  // W tile, widened
+  __shared__ double sb[2][BKK][BN + 1];  // Ghat tile
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int N = K;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  double c[4][4][2] = {};
+
+  auto load_tiles = [&](int buf, int k0) {
+    for (int e = threadIdx.x; e < BM * BKK; e += 128) {
+      const int r = e / BKK, kk = e % BKK;
+      const int gm = m0 + r, gk = k0 + kk;
+      sa[buf][r][kk] = (gm < M && gk < K) ? (double)w[(int64_t)gm * ldw + gk] : 0.0;
+    }
+    for (int e = threadIdx.x; e < BKK * BN; e += 128) {
+      const int kk = e / BN, cc = e % BN;
+      const int gk = k0 + kk, gn = n0 + cc;
+      sb[buf][kk][cc] =
+          (gk < K && gn < N) ? scaled_g((double)g[(int64_t)gk * ldg + gn], gk == gn, alpha, oma) : 0.0;
+    }
+  };
+
+  const int nk = (K + BKK - 1) / BKK;
+  load_tiles(0, 0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles(buf ^ 1, (kt + 1) * BKK);
+#pragma unroll
+    for (int ks = 0; ks < BKK; ks += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sa[buf][wm + i * 8 + (lane >> 2)][ks + (lane & 3)];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sb[buf][ks + (lane & 3)][wn + j * 8 + (lane >> 2)];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma(c[i][j][0], c[i][j][1], a[i], b[j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = m0 + wm + i * 8 + (lane >> 2);
+      const int cc = n0 + wn + j * 8 + (lane & 3) * 2;
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (r < M && cc + u < N) {
+          double* o = acc + (int64_t)r * ldacc + cc + u;
+          *o = accumulate ? __dadd_rn(*o, c[i][j][u]) : c[i][j][u];
+        }
+    }
+}
+
+// ---- cuSOLVER through dlopen (off the hot path; keeps libvlmerge loadable without it) ----------
+typedef void* cusolverDnHandle_t;
+typedef int cusolverStatus_t;
+struct Cusolver {
+  void* lib = nullptr;
+  cusolverStatus_t (*create)(cusolverDnHandle_t*) = nullptr;
+  cusolverStatus_t (*set_stream)(cusolverDnHandle_t, cudaStream_t) = nullptr;
+  cusolverStatus_t (*potrf_bufsize)(cusolverDnHandle_t, int, int, double*, int, int*) = nullptr;
+  cusolverStatus_t (*potrf)(cusolverDnHandle_t, int, int, double*, int, double*, int, int*) = nullptr;
+  cusolverStatus_t (*potrs)(cusolverDnHandle_t, int, int, int, const double*, int, double*, int, int*) = nullptr;
+  cusolverDnHandle_t handle[64] = {};
+};
+Cusolver g_cs;
+std::mutex g_cs_mu;
+
+int load_cusolver() {
+  if (g_cs.lib) return 0;
+  const char* names[] = {"libcusolver.so.11", "libcusolver.so", "/usr/local/cuda/lib64/libcusolver.so.11",
+                         "libcusolver.so.12"};
+  for (const char* n : names) {
+    g_cs.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_cs.lib) break;
+  }
+  VLM_REQUIRE(g_cs.lib != nullptr, VLM_ERR_DRIVER, "cannot dlopen libcusolver: %s", dlerror());
+#define VLM_SYM(field, name)                                              \
+  g_cs.field = reinterpret_cast<decltype(g_cs.field)>(dlsym(g_cs.lib, name)); \
+  VLM_REQUIRE(g_cs.field != nullptr, VLM_ERR_DRIVER, "libcusolver lacks %s", name)
+  VLM_SYM(create, "cusolverDnCreate");
+  VLM_SYM(set_stream, "cusolverDnSetStream");
+  VLM_SYM(potrf_bufsize, "cusolverDnDpotrf_bufferSize");
+  VLM_SYM(potrf, "cusolverDnDpotrf");
+  VLM_SYM(potrs, "cusolverDnDpotrs");
+#undef VLM_SYM
+  return 0;
+}
+
+}  // namespace
+}  // namespace vlm
+
+using namespace vlm;
+
+extern "C" int vlm_gram_scale_accum(const void* g, int g_dtype, int d, int64_t ldg, double alpha, double* out,
+                                    int64_t ldo, int accumulate, void* stream) {
+  VLM_REQUIRE(g && out && d > 0 && ldg >= d && ldo >= d, VLM_ERR_INVALID_ARG, "vlm_gram_scale_accum: bad arguments");
+  VLM_REQUIRE(g_dtype == VLM_F64 || g_dtype == VLM_F32, VLM_ERR_INVALID_ARG,
+              "vlm_gram_scale_accum: g_dtype must be VLM_F64 or VLM_F32");
+  const int64_t n = (int64_t)d * d;
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  auto s = static_cast<cudaStream_t>(stream);
+  if (g_dtype == VLM_F64)
+    gram_scale_accum_kernel<double>
+        <<<grid, 256, 0, s>>>(static_cast<const double*>(g), d, ldg, alpha, 1.0 - alpha, out, ldo, accumulate);
+  else
+    gram_scale_accum_kernel<float>
+        <<<grid, 256, 0, s>>>(static_cast<const float*>(g), d, ldg, alpha, 1.0 - alpha, out, ldo, accumulate);
+  VLM_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int vlm_regmean_rhs(const float* w, int out_f, int in_f, int64_t ldw, const void* g, int g_dtype,
+                               int64_t ldg, double alpha, double* acc, int64_t ldacc, int accumulate, void* stream) {
+  VLM_REQUIRE(w && g && acc && out_f > 0 && in_f > 0 && ldw >= in_f && ldg >= in_f && ldacc >= in_f,
+              VLM_ERR_INVALID_ARG, "vlm_regmean_rhs: bad arguments");
+  VLM_REQUIRE(g_dtype == VLM_F64 || g_dtype == VLM_F32, VLM_ERR_INVALID_ARG,
+              "vlm_regmean_rhs: g_dtype must be VLM_F64 or VLM_F32");
+  dim3 grid((in_f + BN - 1) / BN, (out_f + BM - 1) / BM);
+  auto s = static_cast<cudaStream_t>(stream);
+  if (g_dtype == VLM_F64)
+    regmean_rhs_kernel<double><<<grid, 128, 0, s>>>(w, out_f, in_f, ldw, static_cast<const double*>(g), ldg, alpha,
+                                                    1.0 - alpha, acc, ldacc, accumulate);
+  else
+    regmean_rhs_kernel<float><<<grid, 128, 0, s>>>(w, out_f, in_f, ldw, static_cast<const float*>(g), ldg, alpha,
+                                                   1.0 - alpha, acc, ldacc, accumulate);
+  VLM_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int vlm_spd_solve_right(double* s, int in_f, int64_t lds, double* r, int out_f, int64_t ldr,
+                                   void* stream) {
+  VLM_REQUIRE(s && r && in_f > 0 && out_f > 0 && lds >= in_f && ldr >= in_f, VLM_ERR_INVALID_ARG,
+              "vlm_spd_solve_right: bad arguments");
+  int dev = 0;
+  VLM_CUDA(cudaGetDevice(&dev));
+  VLM_REQUIRE(dev < 64, VLM_ERR_UNSUPPORTED, "device index %d out of range", dev);
+  auto st = static_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lk(g_cs_mu);
+  if (int rc = load_cusolver()) return rc;
+  if (!g_cs.handle[dev])
+    VLM_REQUIRE(g_cs.create(&g_cs.handle[dev]) == 0, VLM_ERR_DRIVER, "cusolverDnCreate failed");
+  cusolverDnHandle_t h = g_cs.handle[dev];
+  VLM_REQUIRE(g_cs.set_stream(h, st) == 0, VLM_ERR_DRIVER, "cusolverDnSetStream failed");
+  // Row-major symmetric S is also column-major S.  Row-major R (out_f x in_f) read column-major is
+  // R^T (in_f x out_f), and S * X^T = R^T  <=>  X = R * S^{-1}: potrs leaves X row-major in r.
+  const int uplo_lower = 0;  // CUBLAS_FILL_MODE_LOWER
+  int lwork = 0;
+  VLM_REQUIRE(g_cs.potrf_bufsize(h, uplo_lower, in_f, s, (int)lds, &lwork) == 0, VLM_ERR_DRIVER,
+              "cusolverDnDpotrf_bufferSize failed");
+  double* work = nullptr;
+  int* info = nullptr;
+  VLM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&work), sizeof(double) * (size_t)std::max(lwork, 1), st));
+  VLM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&info), sizeof(int) * 2, st));
+  cusolverStatus_t cs1 = g_cs.potrf(h, uplo_lower, in_f, s, (int)lds, work, lwork, info);
+  cusolverStatus_t cs2 = g_cs.potrs(h, uplo_lower, in_f, out_f, s, (int)lds, r, (int)ldr, info + 1);
+  count_launch(2);
+  int info_host[2] = {0, 0};
+  cudaError_t e = cudaMemcpyAsync(info_host, info, sizeof(info_host), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFreeAsync(work, st);
+  cudaFreeAsync(info, st);
+  if (e != cudaSuccess) return fail((int)e, "vlm_spd_solve_right: %s", cudaGetErrorString(e));
+  VLM_REQUIRE(cs1 == 0 && cs2 == 0, VLM_ERR_INTERNAL, "cuSOLVER potrf/potrs status %d/%d", cs1, cs2);
+  VLM_REQUIRE(info_host[0] == 0, VLM_ERR_NOT_SPD,
+              "summed Gram is not positive definite (leading minor %d); calibrate with more rows than "
+              "features or use scaling_for_non_diag < 1",
+              info_host[0]);
+  VLM_REQUIRE(info_host[1] == 0, VLM_ERR_INTERNAL, "cusolverDnDpotrs info %d", info_host[1]);
+  return 0;
+}

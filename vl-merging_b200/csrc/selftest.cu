@@ -1,0 +1,389 @@
+// selftest.cu — native smoke/benchmark of libvlmerge on a B200, independent of Python.
+//   build/selftest [quick|full]
+// For every kernel it checks the result against a host fp64 computation (or the SIMT kernel for
+// the large SYRK shapes) and prints one line per case: rel. Frobenius error, time, TFLOP/s or GB/s.
+// Exit code = number of failed cases.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/vlmerge.h"
+
+#define CK(x)                                                                             \
+  do {                                                                                    \
+    cudaError_t e_ = (x);                                                                 \
+    if (e_ != cudaSuccess) {                                                              \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__);     \
+      exit(99);                                                                           \
+    }                                                                                     \
+  } while (0)
+#define VK(x)                                                              \
+  do {                                                                     \
+    int r_ = (x);                                                          \
+    if (r_ != 0) {                                                         \
+      printf("vlm error %d: %s (%s:%d)\n", r_, vlm_last_error(), __FILE__, __LINE__); \
+      exit(98);                                                            \
+    }                                                                      \
+  } while (0)
+
+static uint64_t g_rng = 0x9E3779B97F4A7C15ull;
+static inline float frand() {  // uniform (-1, 1)
+  g_rng = g_rng * 6364136223846793005ull + 1442695040888963407ull;
+  return (float)((g_rng >> 40) & 0xFFFFFF) / 8388608.0f - 1.0f;
+}
+
+static int g_fail = 0;
+
+struct Timer {
+  cudaEvent_t a, b;
+  Timer() {
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+  }
+  void start() { CK(cudaEventRecord(a)); }
+  float stop() {
+    CK(cudaEventRecord(b));
+    CK(cudaEventSynchronize(b));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    return ms;
+  }
+};
+
+// ---- SYRK ----------------------------------------------------------------------------------
+template <typename T>
+static void fill_x(std::vector<T>& h, int mode);
+template <>
+void fill_x<float>(std::vector<float>& h, int mode) {
+  for (auto& v : h) {
+    float f = frand();
+    v = mode == 1 ? fabsf(f) + 0.25f : f;
+  }
+}
+template <>
+void fill_x<__nv_bfloat16>(std::vector<__nv_bfloat16>& h, int mode) {
+  for (auto& v : h) {
+    float f = frand();
+    v = __float2bfloat16(mode == 1 ? fabsf(f) + 0.25f : f);
+  }
+}
+template <>
+void fill_x<__half>(std::vector<__half>& h, int mode) {
+  for (auto& v : h) {
+    float f = frand();
+    v = __float2half(mode == 1 ? fabsf(f) + 0.25f : f);
+  }
+}
+static inline double to_d(float v) { return v; }
+static inline double to_d(__nv_bfloat16 v) { return __bfloat162float(v); }
+static inline double to_d(__half v) { return __half2float(v); }
+
+// compares the upper triangle of two d x d matrices; returns rel. Frobenius error
+static double upper_rel_err(const std::vector<float>& a, const std::vector<double>& ref, int d, double* max_abs,
+                            int* wr, int* wc) {
+  double num = 0, den = 0;
+  *max_abs = 0;
+  *wr = *wc = -1;
+  for (int r = 0; r < d; ++r)
+    for (int c = r; c < d; ++c) {
+      const double x = a[(size_t)r * d + c], y = ref[(size_t)r * d + c];
+      const double e = x - y;
+      num += e * e;
+      den += y * y;
+      if (fabs(e) > *max_abs) {
+        *max_abs = fabs(e);
+        *wr = r;
+        *wc = c;
+      }
+    }
+  return sqrt(num / (den > 0 ? den : 1));
+}
+
+template <typename T>
+static void syrk_case(const char* name, int dtype, int64_t rows, int d, int mode, bool host_ref, int iters,
+                      double tol) {
+  const int64_t ldx = d;
+  std::vector<T> hx((size_t)rows * d);
+  fill_x<T>(hx, mode);
+  T* dx;
+  float *g_tc, *g_ref;
+  CK(cudaMalloc(&dx, hx.size() * sizeof(T)));
+  CK(cudaMalloc(&g_tc, (size_t)d * d * 4));
+  CK(cudaMalloc(&g_ref, (size_t)d * d * 4));
+  CK(cudaMemcpy(dx, hx.data(), hx.size() * sizeof(T), cudaMemcpyHostToDevice));
+  CK(cudaMemset(g_tc, 0, (size_t)d * d * 4));
+  CK(cudaMemset(g_ref, 0, (size_t)d * d * 4));
+
+  std::vector<double> ref((size_t)d * d, 0.0);
+  if (host_ref) {
+    for (int64_t k = 0; k < rows; ++k) {
+      const T* xr = &hx[(size_t)k * d];
+      for (int r = 0; r < d; ++r) {
+        const double a = to_d(xr[r]);
+        double* o = &ref[(size_t)r * d];
+        for (int c = r; c < d; ++c) o[c] += a * to_d(xr[c]);
+      }
+    }
+  } else {
+    VK(vlm_syrk_accum_simt(dx, dtype, rows, d, ldx, g_ref, d, nullptr));
+    CK(cudaDeviceSynchronize());
+    std::vector<float> tmp((size_t)d * d);
+    CK(cudaMemcpy(tmp.data(), g_ref, tmp.size() * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < tmp.size(); ++i) ref[i] = tmp[i];
+  }
+
+  // two accumulating calls: checks "+=" across calls as well (reference doubled)
+  VK(vlm_syrk_accum(dx, dtype, rows, d, ldx, g_tc, d, nullptr));
+  VK(vlm_syrk_accum(dx, dtype, rows, d, ldx, g_tc, d, nullptr));
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("SYRK %-28s KERNEL FAILED: %s\n", name, cudaGetErrorString(e));
+    exit(97);
+  }
+  std::vector<float> out((size_t)d * d);
+  CK(cudaMemcpy(out.data(), g_tc, out.size() * 4, cudaMemcpyDeviceToHost));
+  for (auto& v : ref) v *= 2.0;
+  double max_abs;
+  int wr, wc;
+  const double err = upper_rel_err(out, ref, d, &max_abs, &wr, &wc);
+
+  // finalize: mirror check
+  VK(vlm_sym_finalize(g_tc, d, d, nullptr, 0, nullptr));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out.data(), g_tc, out.size() * 4, cudaMemcpyDeviceToHost));
+  size_t asym = 0;
+  for (int r = 0; r < d; ++r)
+    for (int c = 0; c < r; ++c) asym += out[(size_t)r * d + c] != out[(size_t)c * d + r];
+
+  float ms = 0;
+  if (iters > 0) {
+    Timer t;
+    for (int i = 0; i < 3; ++i) VK(vlm_syrk_accum(dx, dtype, rows, d, ldx, g_tc, d, nullptr));
+    t.start();
+    for (int i = 0; i < iters; ++i) VK(vlm_syrk_accum(dx, dtype, rows, d, ldx, g_tc, d, nullptr));
+    ms = t.stop() / iters;
+  }
+  const double flops = (double)rows * d * (d + 1.0);  // symmetric count
+  const bool ok = err <= tol && asym == 0 && std::isfinite(err);
+  printf("SYRK %-28s rows=%-6lld d=%-5d relF=%.3e maxabs=%.3e@(%d,%d) asym=%zu  %.3f ms  %.1f TFLOP/s(sym)  %s\n",
+         name, (long long)rows, d, err, max_abs, wr, wc, asym, ms, ms > 0 ? flops / ms * 1e-9 : 0.0,
+         ok ? "OK" : "FAIL");
+  if (!ok) {
+    ++g_fail;
+    // a few samples to help diagnose layout mistakes
+    for (int r = 0; r < 2; ++r)
+      for (int c : {r, r + 1, 31, 32, 127, 128, 255, 256}) {
+        if (c < d && c >= r) printf("   G[%d][%d] got %.6g want %.6g\n", r, c, out[(size_t)r * d + c], ref[(size_t)r * d + c]);
+      }
+  }
+  CK(cudaFree(dx));
+  CK(cudaFree(g_tc));
+  CK(cudaFree(g_ref));
+}
+
+// ---- merge ---------------------------------------------------------------------------------
+static void merge_case(const char* name, int mode, int n_src, size_t n, size_t misalign, int iters) {
+  std::vector<std::vector<float>> hs(n_src, std::vector<float>(n));
+  for (auto& v : hs)
+    for (auto& x : v) x = frand();
+  float coef[4] = {0.5f, 0.5f, 1.0f / 3, 0.25f};
+  if (mode == VLM_MERGE_SEQ_LERP) coef[1] = coef[2] = coef[3] = 0.75f;
+  std::vector<float*> ds(n_src);
+  for (int m = 0; m < n_src; ++m) {
+    CK(cudaMalloc(&ds[m], (n + 8) * 4));
+    CK(cudaMemcpy(ds[m] + misalign, hs[m].data(), n * 4, cudaMemcpyHostToDevice));
+  }
+  float* dd;
+  CK(cudaMalloc(&dd, (n + 8) * 4));
+  vlm_merge_seg seg;
+  memset(&seg, 0, sizeof(seg));
+  seg.dst = dd + misalign;
+  for (int m = 0; m < n_src; ++m) {
+    seg.src[m] = ds[m] + misalign;
+    seg.coef[m] = coef[m];
+  }
+  seg.n = n;
+  seg.n_src = n_src;
+  seg.mode = mode;
+  // split into several segments to exercise the chunk table
+  std::vector<vlm_merge_seg> segs;
+  size_t off = 0;
+  const size_t parts[4] = {n / 2, n / 4, 777 < n ? 777 : 0, 0};
+  for (int p = 0; p < 4; ++p) {
+    size_t len = p == 3 ? n - off : (parts[p] / 4) * 4;
+    if (len == 0) continue;
+    vlm_merge_seg s2 = seg;
+    s2.dst = seg.dst + off;
+    for (int m = 0; m < n_src; ++m) s2.src[m] = seg.src[m] + off;
+    s2.n = len;
+    segs.push_back(s2);
+    off += len;
+  }
+  vlm_merge_plan* plan;
+  VK(vlm_merge_plan_create(segs.data(), (int)segs.size(), &plan));
+  VK(vlm_merge_plan_run(plan, nullptr));
+  CK(cudaDeviceSynchronize());
+  std::vector<float> out(n);
+  CK(cudaMemcpy(out.data(), dd + misalign, n * 4, cudaMemcpyDeviceToHost));
+  size_t bad = 0;
+  for (size_t i = 0; i < n; ++i) {
+    volatile float acc;
+    if (mode == VLM_MERGE_WSUM) {
+      acc = coef[0] * hs[0][i];
+      for (int m = 1; m < n_src; ++m) {
+        volatile float p = coef[m] * hs[m][i];
+        acc = acc + p;
+      }
+    } else if (mode == VLM_MERGE_SEQ_LERP) {
+      acc = hs[0][i];
+      for (int m = 1; m < n_src; ++m) {
+        volatile float dlt = hs[m][i] - acc;
+        volatile float p = coef[m] * dlt;
+        acc = acc + p;
+      }
+    } else {
+      acc = hs[0][i];
+      for (int m = 1; m < n_src; ++m) acc = acc + hs[m][i];
+      acc = acc / (float)n_src;
+    }
+    bad += memcmp((const void*)&acc, &out[i], 4) != 0;
+  }
+  float ms = 0;
+  if (iters > 0) {
+    Timer t;
+    for (int i = 0; i < 3; ++i) VK(vlm_merge_plan_run(plan, nullptr));
+    t.start();
+    for (int i = 0; i < iters; ++i) VK(vlm_merge_plan_run(plan, nullptr));
+    ms = t.stop() / iters;
+  }
+  const double gb = (double)vlm_merge_plan_bytes(plan) * 1e-9;
+  printf("MERGE %-24s n=%-10zu src=%d misalign=%zu mismatches=%zu  %.3f ms  %.0f GB/s  %s\n", name, n, n_src,
+         misalign, bad, ms, ms > 0 ? gb / (ms * 1e-3) : 0.0, bad == 0 ? "OK" : "FAIL");
+  if (bad) ++g_fail;
+  VK(vlm_merge_plan_destroy(plan));
+  for (auto p : ds) CK(cudaFree(p));
+  CK(cudaFree(dd));
+}
+
+// ---- regmean -------------------------------------------------------------------------------
+static void regmean_case(int out_f, int in_f, double alpha) {
+  // G = Y^T Y + I (SPD), W random
+  const int rows = in_f + 64;
+  std::vector<double> y((size_t)rows * in_f), G((size_t)in_f * in_f, 0.0);
+  for (auto& v : y) v = frand();
+  for (int k = 0; k < rows; ++k)
+    for (int r = 0; r < in_f; ++r)
+      for (int c = 0; c < in_f; ++c) G[(size_t)r * in_f + c] += y[(size_t)k * in_f + r] * y[(size_t)k * in_f + c];
+  std::vector<float> W((size_t)out_f * in_f);
+  for (auto& v : W) v = frand();
+  std::vector<double> Gh(G);
+  for (int r = 0; r < in_f; ++r)
+    for (int c = 0; c < in_f; ++c)
+      Gh[(size_t)r * in_f + c] =
+          r == c ? alpha * G[(size_t)r * in_f + c] + (1 - alpha) * G[(size_t)r * in_f + c] : alpha * G[(size_t)r * in_f + c];
+  std::vector<double> R((size_t)out_f * in_f, 0.0);
+  for (int o = 0; o < out_f; ++o)
+    for (int k = 0; k < in_f; ++k) {
+      const double w = W[(size_t)o * in_f + k];
+      for (int c = 0; c < in_f; ++c) R[(size_t)o * in_f + c] += w * Gh[(size_t)k * in_f + c];
+    }
+  double *dG, *dS, *dR;
+  float* dW;
+  CK(cudaMalloc(&dG, G.size() * 8));
+  CK(cudaMalloc(&dS, G.size() * 8));
+  CK(cudaMalloc(&dR, R.size() * 8));
+  CK(cudaMalloc(&dW, W.size() * 4));
+  CK(cudaMemcpy(dG, G.data(), G.size() * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice));
+  VK(vlm_gram_scale_accum(dG, VLM_F64, in_f, in_f, alpha, dS, in_f, 0, nullptr));
+  VK(vlm_regmean_rhs(dW, out_f, in_f, in_f, dG, VLM_F64, in_f, alpha, dR, in_f, 0, nullptr));
+  CK(cudaDeviceSynchronize());
+  std::vector<double> gotR(R.size()), gotS(G.size());
+  CK(cudaMemcpy(gotR.data(), dR, R.size() * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(gotS.data(), dS, G.size() * 8, cudaMemcpyDeviceToHost));
+  double num = 0, den = 0, sbad = 0;
+  for (size_t i = 0; i < R.size(); ++i) {
+    num += (gotR[i] - R[i]) * (gotR[i] - R[i]);
+    den += R[i] * R[i];
+  }
+  for (size_t i = 0; i < G.size(); ++i) sbad += gotS[i] != Gh[i];
+  const double rhs_err = sqrt(num / den);
+  // solve: X = R * S^-1  =>  X * S == R
+  VK(vlm_spd_solve_right(dS, in_f, in_f, dR, out_f, in_f, nullptr));
+  std::vector<double> X(R.size());
+  CK(cudaMemcpy(X.data(), dR, R.size() * 8, cudaMemcpyDeviceToHost));
+  num = 0;
+  for (int o = 0; o < out_f; ++o)
+    for (int c = 0; c < in_f; ++c) {
+      double acc = 0;
+      for (int k = 0; k < in_f; ++k) acc += X[(size_t)o * in_f + k] * Gh[(size_t)k * in_f + c];
+      const double e = acc - R[(size_t)o * in_f + c];
+      num += e * e;
+    }
+  const double solve_err = sqrt(num / den);
+  const bool ok = rhs_err < 1e-13 && sbad == 0 && solve_err < 1e-10;
+  printf("REGMEAN out=%d in=%d alpha=%.2f rhs_relF=%.2e scaleG_mismatch=%.0f solve_residual=%.2e  %s\n", out_f, in_f,
+         alpha, rhs_err, sbad, solve_err, ok ? "OK" : "FAIL");
+  if (!ok) ++g_fail;
+  CK(cudaFree(dG));
+  CK(cudaFree(dS));
+  CK(cudaFree(dR));
+  CK(cudaFree(dW));
+}
+
+int main(int argc, char** argv) {
+  const bool full = argc > 1 && !strcmp(argv[1], "full");
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  printf("device: %s, %d SMs, cc %d.%d, vlm abi %d\n", prop.name, prop.multiProcessorCount, prop.major, prop.minor,
+         vlm_version());
+
+  // merge first: simplest kernel
+  merge_case("wsum2", VLM_MERGE_WSUM, 2, 1 << 20, 0, 0);
+  merge_case("wsum3", VLM_MERGE_WSUM, 3, (1 << 20) + 3, 0, 0);
+  merge_case("seqlerp3", VLM_MERGE_SEQ_LERP, 3, (1 << 18) + 1, 0, 0);
+  merge_case("seqlerp4", VLM_MERGE_SEQ_LERP, 4, (1 << 18), 0, 0);
+  merge_case("mean2", VLM_MERGE_MEAN, 2, 4099, 0, 0);
+  merge_case("mean3-misaligned", VLM_MERGE_MEAN, 3, 70001, 1, 0);
+  merge_case("wsum2-misaligned", VLM_MERGE_WSUM, 2, 70001, 3, 0);
+
+  regmean_case(96, 128, 1.0);
+  regmean_case(200, 192, 0.9);
+
+  // SYRK: small shapes against a host fp64 Gram
+  syrk_case<float>("f32 1 tile", VLM_F32, 64, 128, 0, true, 0, 2e-3);
+  syrk_case<float>("f32 wide tile", VLM_F32, 200, 256, 0, true, 0, 2e-3);
+  syrk_case<float>("f32 d=768 ragged rows", VLM_F32, 1000, 768, 0, true, 0, 2e-3);
+  syrk_case<float>("f32 d=200 ragged cols", VLM_F32, 333, 200, 1, true, 0, 2e-3);
+  syrk_case<float>("f32 d=900 oob group", VLM_F32, 130, 900, 0, true, 0, 2e-3);
+  syrk_case<__nv_bfloat16>("bf16 d=768", VLM_BF16, 1000, 768, 0, true, 0, 1e-5);
+  syrk_case<__half>("f16 d=768 positive", VLM_F16, 1000, 768, 1, true, 0, 1e-5);
+  syrk_case<__nv_bfloat16>("bf16 d=200 ragged", VLM_BF16, 77, 200, 1, true, 0, 1e-5);
+  syrk_case<float>("f32 d=768 positive", VLM_F32, 2560, 768, 1, true, 0, 2e-3);
+
+  // hot shapes: SIMT kernel as the reference, timed
+  syrk_case<float>("f32 text d=768", VLM_F32, 2560, 768, 0, false, 20, 2e-3);
+  syrk_case<float>("f32 text d=3072", VLM_F32, 2560, 3072, 1, false, 20, 2e-3);
+  syrk_case<float>("f32 image d=768", VLM_F32, 36928, 768, 0, false, 20, 2e-3);
+  syrk_case<float>("f32 image d=3072", VLM_F32, 36928, 3072, 1, false, 10, 2e-3);
+  syrk_case<__nv_bfloat16>("bf16 image d=768", VLM_BF16, 36928, 768, 0, false, 20, 1e-4);
+  syrk_case<__nv_bfloat16>("bf16 image d=3072", VLM_BF16, 36928, 3072, 1, false, 10, 1e-4);
+  if (full) {
+    syrk_case<float>("f32 image d=1024", VLM_F32, 36928, 1024, 0, false, 20, 2e-3);
+    syrk_case<float>("f32 image d=4096", VLM_F32, 36928, 4096, 1, false, 10, 2e-3);
+    syrk_case<__half>("f16 image d=4096", VLM_F16, 36928, 4096, 1, false, 10, 1e-4);
+  }
+
+  // merge bandwidth at the VLMo-base size: 2 sources x 85 M elements -> 1.02 GB moved
+  merge_case("wsum2 85M (base ufo)", VLM_MERGE_WSUM, 2, 85045248, 0, 20);
+  merge_case("seqlerp3 85M", VLM_MERGE_SEQ_LERP, 3, 85045248, 0, 20);
+
+  printf("launches=%llu failed=%d\n", (unsigned long long)vlm_launch_count(), g_fail);
+  return g_fail;
+}
