@@ -5,9 +5,11 @@
 //
 // Layout.  X is the hooked activation viewed as [rows, d] row-major, so for G = X^T X the contraction
 // dimension (rows) is the SLOW one: both MMA operands are MN-major.  One TMA box is {128 bytes of
-// columns, BK rows} with the 128-byte swizzle, which is exactly one column-group of the canonical
-// MN-major SWIZZLE_128B UMMA layout  ((T,8,m),(8,k)) : ((1,T,LBO),(8T,SBO)):
-//   LBO = BK*128 bytes (next 128-byte column group = next TMA box), SBO = 1024 bytes (next 8 rows).
+// columns, BK rows} with a 128-byte swizzle, which is exactly one column-group of the canonical
+// MN-major UMMA layout  ((T,8,m),(R,k)) : ((1,T,LBO),(8T,SBO)):
+//   LBO = BK*128 bytes (next 128-byte column group = next TMA box), SBO = R*128 bytes (next R rows);
+//   R = 8 rows (SWIZZLE_128B) for bf16/f16, R = 4 rows (SWIZZLE_128B_BASE32B, TMA ..._ATOM_32B) for
+//   TF32 — the only swizzled layout the tensor core takes for MN-major 32-bit operands.
 // A 128-column block of X for one stage is therefore always 16 KB (fp32: 4 boxes x 32 rows,
 // bf16/f16: 2 boxes x 64 rows) and one stage holds [B block 0][B block 1][A block].
 //
@@ -52,17 +54,24 @@ struct Geo {
   static constexpr int UMMA_K = 32 / ELEM_BYTES;    // rows per tcgen05.mma: 8 (tf32) / 16 (f16)
   static constexpr int KSTEP_BYTES = UMMA_K * 128;  // smem advance per MMA
   static constexpr int NUM_MMA = BK / UMMA_K;       // 4
+  // rows per swizzle atom: 8 (SWIZZLE_128B) for 16-bit operands, 4 (SWIZZLE_128B_BASE32B) for TF32
+  static constexpr int LAYOUT_TYPE = ELEM_BYTES == 4 ? 1 : 2;
+  static constexpr int SBO_BYTES = ELEM_BYTES == 4 ? 512 : 1024;
   static_assert(GB * BOX_BYTES == kBlockBytes, "block geometry");
 };
 
-// UMMA shared-memory descriptor, SWIZZLE_128B, MN-major canonical layout (see header comment).
+// UMMA shared-memory descriptor for the MN-major canonical layouts (see header comment).
+// layout_type 2 = SWIZZLE_128B (16-byte chunks XOR row%8, 8-row atoms: bf16/f16),
+// layout_type 1 = SWIZZLE_128B_BASE32B (32-byte chunks XOR row%4, 4-row atoms): the only swizzled
+// layout tcgen05 accepts for MN-major TF32 operands; its TMA twin is SWIZZLE_128B_ATOM_32B.
+template <int LAYOUT_TYPE>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);             // start address      bits [0,14)
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;    // leading byte off.  bits [16,30)
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;    // stride byte off.   bits [32,46)
   d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell) bits [46,48)
-  d |= (uint64_t)2 << 61;                               // layout type SWIZZLE_128B  bits [61,64)
+  d |= (uint64_t)LAYOUT_TYPE << 61;                     // layout type        bits [61,64)
   return d;
 }
 
@@ -188,8 +197,8 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         const uint32_t sa = diag ? sb : sb + 2 * kBlockBytes;
 #pragma unroll
         for (int kk = 0; kk < G::NUM_MMA; ++kk) {
-          const uint64_t adesc = make_smem_desc(sa + kk * G::KSTEP_BYTES, G::BOX_BYTES, 1024);
-          const uint64_t bdesc = make_smem_desc(sb + kk * G::KSTEP_BYTES, G::BOX_BYTES, 1024);
+          const uint64_t adesc = make_smem_desc<G::LAYOUT_TYPE>(sa + kk * G::KSTEP_BYTES, G::BOX_BYTES, G::SBO_BYTES);
+          const uint64_t bdesc = make_smem_desc<G::LAYOUT_TYPE>(sb + kk * G::KSTEP_BYTES, G::BOX_BYTES, G::SBO_BYTES);
           umma<FMT>(d_tmem, adesc, bdesc, idesc, (k > seg.k0 || kk > 0) ? 1u : 0u);
         }
         tc_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
@@ -400,8 +409,9 @@ int syrk_tc_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, f
     cuuint64_t gstr[1] = {(cuuint64_t)ldx * elem};
     cuuint32_t box[2] = {(cuuint32_t)(128 / elem), (cuuint32_t)bk};
     cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle swz = elem == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
     CUresult r = encode(&tm_x, dt, 2, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VLM_REQUIRE(r == CUDA_SUCCESS, VLM_ERR_DRIVER, "cuTensorMapEncodeTiled(X) failed: CUresult %d", (int)r);
   }
