@@ -1,0 +1,472 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the merge hot path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one calibration batch of RegMean Gram caching for VLMo-base all_moe (configs[1] of
+BASELINE.json): the frozen image and text towers (stock torch) run over B=64 synthetic 384-px images +
+40-token texts per GPU, and every hooked module input goes through GramCache.hook_gram_input ->
+vlm_syrk_accum (96 launches per step).  `value` = samples/s with the batch resident in HBM; `e2e` =
+the same call with the batch in pinned host memory (H2D of images/text and D2H of the logits inside
+the timed region).  N > 1: one process per GPU, batches are data-parallel (weak scaling), and the ONE
+all-reduce of the Gram arena that ends a calibration run is inside the timed region.
+
+Extra objects on the JSON line: `roofline` (the SYRK kernel, tensor-bound), `merge` (kernel (b):
+interpolation of the same checkpoint, GB/s resident and end-to-end, with its own HBM roofline),
+`cpu_baseline` (the reference's CPU path restated in oracle/, timed on this box's host cores).
+
+--impl reference times the reference's CPU implementation of the path (stock forward on the host +
+the reference hook, oracle.reference_hook_torch) on a bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+BATCH_PER_GPU = 64
+ROWS_PER_SAMPLE = 577 + 40
+METRIC = "gram_cache_samples_per_sec"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [ln.split(", ") for t, ln in self.lines if t0 <= t <= t1 + 0.2] or [ln.split(", ") for _, ln in self.lines[-3:]]
+        sm, reasons, smax, power = [], set(), None, []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                smax = float(r[1])
+                power.append(float(r[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "power_w_max": max(power) if power else None, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def syrk_flops(rows, d):
+    return rows * d * (d + 1)  # symmetric count, SURVEY.md §8(d)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    import vl_merging_b200 as vlm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run for N > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    torch.backends.cuda.matmul.allow_tf32 = True   # the frozen forward is stock torch; TF32 matmuls like the SYRK
+    torch.backends.cudnn.allow_tf32 = True
+    peaks = load_peaks()
+
+    cfg = vlm.vlmo_config(args.model)
+    with torch.device(dev):
+        model = vlm.VLMo(cfg)
+    vlm.init_synthetic_(model.eval(), seed=1)
+    amp = {"fp32": None, "bf16": torch.bfloat16, "fp16": torch.float16}[args.autocast]
+
+    class TimedCache(vlm.GramCache):
+        """GramCache that brackets every vlm_syrk_accum launch with CUDA events on the launching stream."""
+        events, timing = [], False
+
+        def accumulate(self, name, x):
+            if not self.timing:
+                return super().accumulate(name, x)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            super().accumulate(name, x)
+            b.record()
+            self.events.append((a, b, x.numel() // x.shape[-1], x.shape[-1], x.dtype))
+
+    cache = TimedCache(dev)
+    cache.register(model, use_moe=True)
+    B = args.batch
+    host_batches = [vlm.synthetic_batch(B, cfg, seed=1234 + rank * 16 + i) for i in range(2)]
+    for hb in host_batches:
+        hb["image"] = [hb["image"][0].pin_memory()]
+        for k in ("text_ids", "text_masks", "text_labels"):
+            hb[k] = hb[k].pin_memory()
+    dev_batches = [{"image": [hb["image"][0].to(dev)], **{k: hb[k].to(dev) for k in ("text_ids", "text_masks", "text_labels")}}
+                   for hb in host_batches]
+
+    def step(batch):
+        with torch.no_grad():
+            if amp is None:
+                return model(batch)
+            with torch.autocast("cuda", dtype=amp):
+                return model(batch)
+
+    def step_e2e(hb):
+        batch = {"image": [hb["image"][0].to(dev, non_blocking=True)],
+                 **{k: hb[k].to(dev, non_blocking=True) for k in ("text_ids", "text_masks", "text_labels")}}
+        return step(batch).float().cpu()   # D2H of the step's result; synchronises
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, with_allreduce):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        for i in range(steps):
+            fn(i)
+        ar_ms = 0.0
+        if with_allreduce and world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            cache.all_reduce(group)
+            e1.record()
+        b.record()
+        barrier()
+        t1 = time.perf_counter()
+        ms = a.elapsed_time(b)
+        if with_allreduce and world > 1:
+            ar_ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, t0, t1, ar_ms
+
+    # ---- warm-up, then the timed region (device-resident inputs) --------------------------------
+    for i in range(max(args.warmup, 3)):
+        step(dev_batches[i % 2])
+    cache.reset()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = vlm._lib.launch_count()
+    cache.timing, cache.events = True, []
+    ms, t0, t1, ar_ms = timed(lambda i: step(dev_batches[i % 2]), args.steps, with_allreduce=True)
+    cache.timing = False
+    launches = vlm._lib.launch_count() - launches0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # per-launch SYRK time, measured live on the launching stream inside the timed region
+    tot_ms = tot_flops = 0.0
+    by_shape = {}
+    for a, b, rows, d, dt in cache.events:
+        dms = a.elapsed_time(b)
+        tot_ms += dms
+        tot_flops += syrk_flops(rows, d)
+        key = f"{rows}x{d}:{str(dt).replace('torch.', '')}"
+        s = by_shape.setdefault(key, [0, 0.0, 0.0])
+        s[0] += 1
+        s[1] += dms
+        s[2] += syrk_flops(rows, d)
+    n_ev = max(len(cache.events), 1)
+    sixteen = amp is not None
+    # TF32 runs at half the bf16 tensor rate; the MEASURED bf16 figure (sustained: kernel timed inside a long step)
+    peak_tf = peaks["bf16_tflops_sustained"] * (1.0 if sixteen else 0.5)
+    achieved_tf = tot_flops / (tot_ms * 1e-3) * 1e-12 if tot_ms > 0 else 0.0
+    roofline = {
+        "kernel": "syrk_tc_kernel (tcgen05 kind::tf32, TMA, TMEM)" if not sixteen else "syrk_tc_kernel (mixed tf32 / f16 kinds under autocast)",
+        "bound": "tensor", "achieved": round(achieved_tf, 2), "peak": round(peak_tf, 1), "unit": "TFLOP/s",
+        "frac": round(achieved_tf / peak_tf, 4), "traffic": None,
+        "peak_source": f"{peaks['source']}: bf16_tflops_sustained{' / 2 (TF32)' if not sixteen else ''}",
+        "flops_per_launch_avg": tot_flops / n_ev, "ms_per_launch_avg": tot_ms / n_ev, "launches_timed": len(cache.events),
+        "syrk_share_of_step": round(tot_ms / (ms if ms > 0 else 1), 4),
+        "by_shape": {k: {"launches": v[0], "ms_avg": round(v[1] / v[0], 4), "tflops": round(v[2] / (v[1] * 1e-3) * 1e-12, 1)}
+                     for k, v in sorted(by_shape.items())},
+    }
+
+    # ---- end to end: host buffers in, logits out, every step --------------------------------------
+    cache.reset()
+    for i in range(2):
+        step_e2e(host_batches[i % 2])
+    ms_e2e, _, _, _ = timed(lambda i: step_e2e(host_batches[i % 2]), args.steps, with_allreduce=True)
+    h2d = sum(host_batches[0][k].numel() * host_batches[0][k].element_size() for k in ("text_ids", "text_masks", "text_labels"))
+    h2d += host_batches[0]["image"][0].numel() * 4
+    e2e = {"value": round(world * B * args.steps / (ms_e2e * 1e-3), 2), "unit": "samples/s",
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * B * 4}
+
+    # ---- Gram parity spot check on the bench's own activations (cheap; not timed) ------------------
+    parity = None
+    if rank == 0:
+        cache.reset()
+        probe = {}
+        mods = dict(model.named_modules())
+        names = ["transformer.blocks.0.attn.v", "transformer.blocks.11.mlp.v.fc2", "transformer.blocks.5.mlp.l.fc1"]
+        hs = [mods[n].register_forward_hook(lambda m, i, o, n=n: probe.__setitem__(
+            n, (lambda x: x.double().reshape(-1, x.shape[-1]).T @ x.double().reshape(-1, x.shape[-1]))(i[0] if isinstance(i, tuple) else i)))
+            for n in names]
+        step(dev_batches[0])
+        for h in hs:
+            h.remove()
+        parity = {n: float(((cache.gram(n).double() - probe[n]).norm() / probe[n].norm()).item()) for n in names}
+        cache.reset()
+
+    # ---- kernel (b): interpolation merge of this checkpoint ---------------------------------------
+    merge = bench_merge(vlm, model, cfg, dev, group, world, rank, peaks, args)
+
+    out = None
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": round(value, 2), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if not sixteen else args.autocast,
+            "data": "synthetic (hash-seeded images U(-1,1) 384px + 40-token ids; random-init VLMo weights)",
+            "config": {"workload": f"RegMean Gram caching, VLMo-{args.model} all_moe, {B} x (577 image + 40 text tokens) per GPU per step; "
+                                   "96 Grams (72 x 768^2 + 24 x 3072^2)" if args.model == "base" else f"RegMean Gram caching, VLMo-{args.model} all_moe",
+                       "global_batch": world * B, "parallelism": f"dp{world}", "forward": "stock torch, " + ("fp32 with TF32 matmuls" if not sixteen else f"autocast {args.autocast}"),
+                       "l2": "inputs larger than L2 (each step streams >2 GB of weights and activations)",
+                       "allreduce_ms_in_timed_region": round(ar_ms, 3)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "merge": merge, "gram_parity_rel_fro": parity,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_sample(args.model, budget_s=25.0)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def bench_merge(vlm, model, cfg, dev, group, world, rank, peaks, args):
+    """Interpolation merge (alpha = 0.5, IRTR-used experts) of the bench checkpoint: kernel-only GB/s with
+    everything resident (one vlm_merge_plan launch), and end to end from pinned host memory and back."""
+    import ctypes
+
+    import torch.distributed as dist
+
+    from vl_merging_b200 import _lib
+    from vl_merging_b200.plan import plan_merge_weights
+
+    mcfg = dict(vlffn_start_layer_index=cfg["vlffn_start_layer_index"], only_activate_used_experts=True, merge_ratio=0.5,
+                loss_names={"irtr": 1, "vqa": 0, "nlvr2": 0})
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    L = cfg["num_layers"]
+    lib = _lib.lib()
+    # resident: build the plan once, time the launch alone (CUDA events on the launching stream)
+    ops = [op for op in plan_merge_weights(sd.keys(), mcfg, L) if not op.passthrough]
+    total = sum(sd[op.srcs[0]].numel() for op in ops)
+    out = torch.empty(total + 4 * len(ops), dtype=torch.float32, device=dev)
+    segs = (_lib.MergeSeg * len(ops))()
+    off = 0
+    for s, op in enumerate(ops):
+        n = sd[op.srcs[0]].numel()
+        segs[s].dst = out.data_ptr() + off * 4
+        for j, k in enumerate(op.srcs):
+            segs[s].src[j] = sd[k].data_ptr()
+            segs[s].coef[j] = op.coefs[j]
+        segs[s].n, segs[s].n_src, segs[s].mode = n, len(op.srcs), op.mode
+        off += (n + 3) // 4 * 4
+    plan = ctypes.c_void_p()
+    _lib.check(lib.vlm_merge_plan_create(segs, len(ops), ctypes.byref(plan)))
+    nbytes = int(lib.vlm_merge_plan_bytes(plan))
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    for _ in range(3):
+        _lib.check(lib.vlm_merge_plan_run(plan, stream))
+    reps = 20
+    evs = []
+    for _ in range(reps):  # bytes moved per launch (1.02 GB) exceed L2, no flush needed
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.check(lib.vlm_merge_plan_run(plan, stream))
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize(dev)
+    ms = sum(a.elapsed_time(b) for a, b in evs) / reps
+    lib.vlm_merge_plan_destroy(plan)
+    gbs = nbytes / (ms * 1e-3) * 1e-9
+
+    # end to end through the public API: pinned host state_dict in, merged host tensors out
+    host_sd = {k: (v.cpu().pin_memory() if "transformer.blocks" in k else v.cpu()) for k, v in sd.items()}
+    vlm.merge_weights(host_sd, mcfg, device=dev, num_layers=L, group=group)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    stats = {}
+    merged = vlm.merge_weights(host_sd, mcfg, device=dev, num_layers=L, group=group, stats=stats)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = t.item()
+    k0 = "transformer.blocks.0.mlp.fc1.weight"
+    ok = torch.equal(merged[k0], 0.5 * host_sd["transformer.blocks.0.mlp.v.fc1.weight"] + 0.5 * host_sd["transformer.blocks.0.mlp.l.fc1.weight"])
+    return {
+        "metric": "merge_GBps", "workload": f"linear interpolation alpha=0.5, VLMo-{args.model} all_moe -> ufo, IRTR-used experts "
+                                            f"({len(ops)} tensors, {nbytes / 1e6:.1f} MB algorithmic: read 2 experts + write 1 per layer)",
+        "value": round(gbs, 1), "unit": "GB/s", "ms_per_launch": round(ms, 4), "launches_per_merge": 1,
+        "roofline": {"kernel": "merge_segments_kernel", "bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "frac": round(gbs / peaks["hbm_gbs"], 4), "traffic": None,
+                     "peak_source": f"{peaks['source']}: hbm_gbs (burst copy)", "frac_of_nominal_8TBps": round(gbs / 8000.0, 4)},
+        "e2e": {"value": round(nbytes / dt * 1e-9, 2), "unit": "GB/s", "seconds": round(dt, 4),
+                "h2d_bytes": stats.get("h2d_bytes"), "d2h_bytes": stats.get("d2h_bytes"), "bit_exact_vs_torch": bool(ok)},
+    }
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_step(model, cfg, batch_size, seed, store):
+    """The reference's CPU implementation of one calibration step: stock forward on the host + the reference
+    hook (fp64 cast, fp64 matmul, host accumulate) restated in oracle.reference_hook_torch."""
+    import vl_merging_b200 as vlm
+
+    batch = vlm.synthetic_batch(batch_size, cfg, seed=seed)
+    with torch.no_grad():
+        model(batch)
+    return batch_size
+
+
+def build_cpu_reference(model_name):
+    import oracle
+    import vl_merging_b200 as vlm
+    from vl_merging_b200.gram import select_hooked_modules
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = vlm.vlmo_config(model_name)
+    model = vlm.init_synthetic_(vlm.VLMo(cfg).eval(), seed=1)
+    store = oracle.new_gram_store()
+    hook = oracle.reference_hook_torch(store)
+    for name, module in select_hooked_modules(model, use_moe=True):
+        module.module_name = name
+        module.register_forward_hook(hook)
+    return cfg, model, store
+
+
+def cpu_baseline_sample(model_name, budget_s=25.0):
+    cfg, model, store = build_cpu_reference(model_name)
+    t0 = time.perf_counter()
+    cpu_reference_step(model, cfg, 1, 0, store)  # warm-up (also sizes the sample)
+    warm = time.perf_counter() - t0
+    n = max(1, min(8, int(budget_s / max(warm, 1e-3)) - 1))
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(n):
+        done += cpu_reference_step(model, cfg, 1, 100 + i, store)
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": round(done / dt, 4), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{done} calibration step(s) of 1 sample (577+40 tokens, 96 fp64 Grams) of the same VLMo-{model_name} workload, "
+                      f"stock forward + reference hook on the host, after 1 warm-up step",
+            "cpu_model": cpu_model_name()}
+
+
+def cpu_model_name():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    cfg, model, store = build_cpu_reference(args.model)
+    per_step = 1  # bounded sample: one sample per step keeps --steps K --warmup W within minutes on the host
+    for i in range(args.warmup):
+        cpu_reference_step(model, cfg, per_step, i, store)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        cpu_reference_step(model, cfg, per_step, 1000 + i, store)
+    dt = time.perf_counter() - t0
+    v = per_step * args.steps / dt
+    sample = f"{per_step} sample per step (577 image + 40 text tokens, 96 fp64 Grams), VLMo-{args.model} all_moe, host cores only"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (same generator as the GPU arm)",
+        "config": {"workload": f"RegMean Gram caching, VLMo-{args.model} all_moe, reference CPU path (stock forward + hook_gram_input "
+                               "restated from src/cache_gram_matrices.py:246-254), bounded sample", "global_batch": per_step,
+                   "parallelism": "host threads"},
+        "cpu_baseline": {"value": round(v, 4), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample, "cpu_model": cpu_model_name()},
+        "e2e": {"value": round(v, 4), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="base", choices=["base", "large", "tiny"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--autocast", default="fp32", choices=["fp32", "bf16", "fp16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,114 @@
+"""GPU parity of kernel (a) through GramCache (forward-hook API -> C ABI) against the oracle
+(oracle.hook_gram_input: the reference's fp64 X^T X).  Tolerance from BASELINE.json: 1e-3 relative
+Frobenius for fp32 activations (TF32 tensor cores, fp32 accumulate); bf16/f16 activations are exact
+on the tensor cores and must meet 2e-5."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+import oracle
+import vl_merging_b200 as vlm
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float32: 1e-3, torch.bfloat16: 2e-5, torch.float16: 2e-5}
+
+
+def rel_fro(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def _x(shape, dtype, seed, positive=False):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(*shape, generator=g)
+    if positive:
+        x = x.abs() + 0.1  # post-GELU-like: non-zero mean
+    return x.to(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape,positive", [((4, 40, 768), False), ((3, 577, 768), True), ((2, 197, 3072), True),
+                                            ((1, 1, 64), False), ((5, 7, 200), False), ((2, 33, 1000), True)])
+def test_hook_matches_oracle(dtype, shape, positive):
+    cache = vlm.GramCache()
+    mod = nn.Identity()
+    mod.module_name = "m"
+    store = oracle.new_gram_store()
+    for call in range(2):  # "+=" across calls
+        x = _x(shape, dtype, seed=call, positive=positive)
+        cache.hook_gram_input(mod, (x.cuda(),), None)      # tuple input, like nn.Module hooks deliver it
+        oracle.hook_gram_input(store, "m", x.float().numpy())
+    out = cache.state_dict()
+    assert list(out.keys()) == ["m"]
+    g = out["m"]
+    assert g.dtype == torch.float64 and g.device.type == "cpu" and g.shape == (shape[-1], shape[-1])
+    assert torch.equal(g, g.T)
+    assert rel_fro(g.numpy(), store["m"]) < TOL[dtype]
+
+
+def test_empty_ragged_and_unaligned_inputs():
+    cache = vlm.GramCache()
+    mod = nn.Identity()
+    mod.module_name = "e"
+    cache.hook_gram_input(mod, torch.zeros(0, 5, 128, device="cuda"), None)   # no rows: no-op
+    assert cache.state_dict()["e"].abs().sum() == 0
+    base = torch.randn(50, 264, device="cuda")
+    views = [base[:, :256], base[:, 1:257], base[::2, 4:260]]   # padded pitch, misaligned start, strided rows
+    store = oracle.new_gram_store()
+    for i, v in enumerate(views):
+        mod.module_name = f"v{i}"
+        cache.hook_gram_input(mod, v, None)
+        oracle.hook_gram_input(store, f"v{i}", v.cpu().numpy())
+    out = cache.state_dict()
+    for i in range(3):
+        assert rel_fro(out[f"v{i}"].numpy(), store[f"v{i}"]) < 1e-3
+
+
+def test_simt_and_tensor_core_paths_agree():
+    x = _x((4, 577, 768), torch.float32, 3).cuda()
+    a, b = vlm.GramCache(), vlm.GramCache(use_simt=True)
+    a.accumulate("g", x)
+    b.accumulate("g", x)
+    ref = (x.double().reshape(-1, 768).T @ x.double().reshape(-1, 768)).cpu().numpy()
+    assert rel_fro(b.state_dict()["g"].numpy(), ref) < 1e-5      # fp32 FMA kernel
+    assert rel_fro(a.state_dict()["g"].numpy(), ref) < 1e-3      # TF32
+
+
+@pytest.mark.parametrize("dtype,d", [(torch.float32, 768), (torch.float32, 3072), (torch.bfloat16, 3072),
+                                     (torch.float16, 1024), (torch.float32, 4096)])
+def test_full_size_properties(dtype, d):
+    """BASELINE sizes (64 images x 577 tokens): fp64 torch Gram as checker + symmetry + trace identity."""
+    rows = 36928
+    x = (_x((rows, d), torch.float32, 11, positive=(d >= 3072)).cuda()).to(dtype)
+    cache = vlm.GramCache()
+    cache.accumulate("g", x.view(64, 577, d))
+    g = cache.gram("g")
+    assert torch.equal(g, g.T)
+    xd = x.double()
+    trace = (xd * xd).sum().item()
+    assert abs(g.double().trace().item() - trace) / trace < TOL[dtype]
+    # 256 full rows of G in fp64 (the whole fp64 Gram of a 4096-wide activation would be 2 TFLOP)
+    idx = torch.arange(0, d, max(1, d // 256), device="cuda")[:256]
+    ref_rows = xd[:, idx].T @ xd
+    err = (g.double()[idx] - ref_rows).norm() / ref_rows.norm()
+    assert err.item() < TOL[dtype]
+
+
+def test_registration_and_reference_file_format(tmp_path):
+    cfg = vlm.vlmo_config("tiny")
+    model = vlm.init_synthetic_(vlm.VLMo(cfg).eval(), seed=1).cuda()
+    cache = vlm.GramCache()
+    names = cache.register(model, use_moe=True)
+    assert len(names) == 116
+    batch = vlm.synthetic_batch(2, cfg, seed=1, device="cuda")
+    with torch.no_grad():
+        model(batch)
+    cache.remove_hooks()
+    cache.save(tmp_path / "tmp.pth")
+    loaded = torch.load(tmp_path / "tmp.pth", map_location="cpu", weights_only=False)
+    assert len(loaded) == 96 and all(v.dtype == torch.float64 for v in loaded.values())
+    assert loaded["transformer.blocks.0.attn.v"].shape == (192, 192)
+    assert loaded["transformer.blocks.11.mlp.l.fc2"].shape == (768, 768)
+    assert not any(".vl" in k for k in loaded)      # vl experts never run in IRTR calibration
+    assert loaded["missing-key"] == 0.0             # still a defaultdict(float), like the reference's

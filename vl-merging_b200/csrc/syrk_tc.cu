@@ -15,15 +15,16 @@
 //
 // Work decomposition.  Output tiles are 128 x (128*w), w in {1,2}, over the block upper triangle
 // (j >= i).  On a diagonal tile the A block IS the first B block, so it is loaded once.  The host
-// builds a per-CTA segment list (syrk_schedule.cpp logic below): whole tiles are dealt round-robin so
-// that all CTAs sweep the rows of X in lock-step (X is read from HBM once and re-read from L2), and
-// the tiles that do not fill a wave are split along K evenly over all CTAs (stream-K).  Every segment
-// ends with an fp32 reduce-add into G, which is also what "G +=" needs across hook calls.
+// builds a per-CTA segment list (build_syrk_schedule below): panel-major stream-K, i.e. all CTAs sweep
+// the rows of X panel by panel (X is read from HBM once and re-read from L2) and the linearised
+// (panel, tile, chunk) space is cut into equal shares.  Every segment ends with an fp32 reduce-add
+// into G, which is also what "G +=" needs across hook calls.
 //
 // Warp roles (256 threads, 1 CTA / SM): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
 // allocator, warps 4-7 = epilogue (TMEM -> registers -> swizzled smem -> cp.reduce.async.bulk.tensor).
 // TMEM holds two 128x256 fp32 accumulators so the epilogue of one segment overlaps the next mainloop.
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -308,55 +309,66 @@ int launch_kernel(int dev, const DeviceSchedule& sched, const CUtensorMap& tm_x,
 }  // namespace
 
 // Exposed for tests (tests/test_schedule.py drives it through vlm_syrk_schedule_host).
+//
+// Panel-major stream-K.  The rows of X are cut into panels of kPanelChunks chunks.  Inside ONE panel
+// the work units are the tiles in row-major order, each costing w * chunks_in_panel, and that linear
+// cost axis is cut into ncta equal contiguous shares; every CTA then moves on to its share of the
+// next panel.  Consequences: (1) at any moment all CTAs read the same row panel of X, so X streams
+// from HBM once and every re-read (each column block is used by ~nb/2 tiles) hits L2; (2) load
+// balance is exact whatever the tile count; (3) no accumulator runs over more than one panel of rows,
+// which bounds the tensor core's truncating fp32 accumulation (the cross-panel sum is the
+// round-to-nearest fp32 reduce-add into G).
 void build_syrk_schedule(int64_t kc, int d, int nsm, std::vector<SyrkSeg>* segs, std::vector<int>* off) {
+  int64_t panel_chunks = 64;  // 2048 fp32 rows / 4096 16-bit rows per panel
+  if (const char* e = getenv("VLM_SYRK_PANEL_CHUNKS")) panel_chunks = std::max(1, atoi(e));
   const int nb = (d + 127) / 128;
   struct Tile {
     int i, j, w;
   };
-  std::vector<Tile> wide, narrow;
+  std::vector<Tile> tiles;
+  int64_t tile_w_sum = 0;
   for (int i = 0; i < nb; ++i)
     for (int j = i; j < nb;) {
       const int w = std::min(2, nb - j);
-      (w == 2 ? wide : narrow).push_back({i, j, w});
+      tiles.push_back({i, j, w});
+      tile_w_sum += w;
       j += w;
     }
-  const int64_t total_cost = (2 * (int64_t)wide.size() + (int64_t)narrow.size()) * kc;
+  const int64_t npanels = (kc + panel_chunks - 1) / panel_chunks;
+  const int64_t total_cost = tile_w_sum * kc;
   // do not split below ~16 chunks of a wide tile per CTA: a segment's epilogue (128 KB reduce-add)
   // must stay small next to its mainloop
   const int64_t min_cost = 32;
-  int ncta = (int)std::max<int64_t>(1, std::min<int64_t>(nsm, total_cost / min_cost));
-  const int nfull = (int)(wide.size() / ncta);  // whole wide tiles per CTA (lock-step sweep over rows)
-  std::vector<Tile> pool(wide.begin() + (size_t)nfull * ncta, wide.end());
-  pool.insert(pool.end(), narrow.begin(), narrow.end());
-  std::vector<int64_t> prefix(pool.size() + 1, 0);
-  for (size_t t = 0; t < pool.size(); ++t) prefix[t + 1] = prefix[t] + (int64_t)pool[t].w * kc;
-  const int64_t pool_cost = prefix.back();
-  auto locate = [&](int64_t b, size_t* t, int64_t* k) {
-    if (b >= pool_cost) {
-      *t = pool.size();
-      *k = 0;
-      return;
+  const int ncta = (int)std::max<int64_t>(1, std::min<int64_t>(nsm, total_cost / min_cost));
+
+  std::vector<std::vector<SyrkSeg>> per_cta(ncta);
+  for (int64_t p = 0; p < npanels; ++p) {
+    const int64_t k_lo = p * panel_chunks, k_hi = std::min(kc, k_lo + panel_chunks);
+    const int64_t panel_cost = tile_w_sum * (k_hi - k_lo);
+    // rotate the CTA that gets the first share so that leftovers do not pile up on CTA 0
+    const int rot = (int)((p * 37) % ncta);
+    int share = 0;
+    int64_t next_cut = panel_cost / ncta;
+    int64_t pos = 0;
+    for (const Tile& t : tiles) {
+      int64_t k = k_lo;
+      while (k < k_hi) {
+        while (share < ncta - 1 && pos >= next_cut) {
+          ++share;
+          next_cut = panel_cost * (share + 1) / ncta;
+        }
+        const int64_t room = (share == ncta - 1) ? (k_hi - k) : (next_cut - pos + t.w - 1) / t.w;
+        const int64_t take = std::min(k_hi - k, std::max<int64_t>(room, 1));
+        per_cta[(share + rot) % ncta].push_back({t.i * 128, t.j * 128, t.w, (int)k, (int)(k + take)});
+        k += take;
+        pos += take * t.w;
+      }
     }
-    size_t lo = std::upper_bound(prefix.begin(), prefix.end(), b) - prefix.begin() - 1;
-    *t = lo;
-    *k = (b - prefix[lo]) / pool[lo].w;
-  };
+  }
   segs->clear();
   off->assign(1, 0);
   for (int c = 0; c < ncta; ++c) {
-    for (int m = 0; m < nfull; ++m) {
-      const Tile& t = wide[(size_t)m * ncta + c];
-      segs->push_back({t.i * 128, t.j * 128, t.w, 0, (int)kc});
-    }
-    size_t t0, t1;
-    int64_t k0, k1;
-    locate(pool_cost * c / ncta, &t0, &k0);
-    locate(pool_cost * (c + 1) / ncta, &t1, &k1);
-    for (size_t t = t0; t <= t1 && t < pool.size(); ++t) {
-      const int64_t a = (t == t0) ? k0 : 0;
-      const int64_t b = (t == t1) ? k1 : kc;
-      if (b > a) segs->push_back({pool[t].i * 128, pool[t].j * 128, pool[t].w, (int)a, (int)b});
-    }
+    segs->insert(segs->end(), per_cta[c].begin(), per_cta[c].end());
     off->push_back((int)segs->size());
   }
 }

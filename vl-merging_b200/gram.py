@@ -1,0 +1,224 @@
+"""gram.py — RegMean Gram-matrix caching, the drop-in for the hook closure of
+src/cache_gram_matrices.py:236-281 and the artefact written at :349.
+
+Reference                                   here
+------------------------------------------  ----------------------------------------------------------
+middle_representations = defaultdict(float)  GramCache (fp32 [d,d] device buffers, one per hooked module)
+hook_gram_input(module, input, output)       GramCache.hook_gram_input — same signature, same use of
+                                             module.module_name; one vlm_syrk_accum launch on the
+                                             current stream instead of fp64 cast + DGEMM + .cpu()
+registration loop (:278-281)                 GramCache.register(model, use_moe)
+torch.save(middle_representations, path)     GramCache.save(path): {name: fp64 CPU (d,d)} — the file
+                                             regmean() loads (vilt_module.py:386)
+(absent: every DDP rank writes its own sums) GramCache.all_reduce(): ONE NCCL all-reduce of the flat arena
+"""
+from collections import defaultdict
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+# src/cache_gram_matrices.py:264-276 (the duplicate entry is the reference's)
+ALL_KEYS_MOE = (
+    "mlp.fc1", "mlp.fc1",
+    "mlp.v.fc1", "mlp.l.fc1", "mlp.vl.fc1", "mlp.v.fc2", "mlp.l.fc2", "mlp.vl.fc2",
+    "attn",
+    "attn.v", "attn.l", "attn.vl",
+    "attn.proj",
+    "attn.v.proj", "attn.l.proj", "attn.vl.proj",
+)
+ALL_KEYS_UFO = ("mlp.fc1", "mlp.fc2", "attn.proj", "norm1", "norm2")
+
+_DTYPES = {torch.float32: _lib.VLM_F32, torch.bfloat16: _lib.VLM_BF16, torch.float16: _lib.VLM_F16}
+
+
+def _in_features(module):
+    """Width of the activation a hooked module receives, if it can be known before the first call."""
+    if isinstance(module, nn.Linear):
+        return module.in_features
+    if isinstance(module, nn.LayerNorm):
+        return module.normalized_shape[-1]
+    qkv = getattr(module, "qkv", None)  # Attention modules: their input is the qkv input
+    if isinstance(qkv, nn.Linear):
+        return qkv.in_features
+    return None
+
+
+def select_hooked_modules(model, use_moe=True, all_keys=None):
+    """The reference's selection rule (src/cache_gram_matrices.py:278-279): every module whose qualified
+    name ends with one of all_keys and does not contain '.bias'.  Returns [(name, module)]."""
+    keys = all_keys if all_keys is not None else (ALL_KEYS_MOE if use_moe else ALL_KEYS_UFO)
+    return [(name, module) for name, module in model.named_modules()
+            if any(name.endswith(k) for k in keys) and ".bias" not in name]
+
+
+def reduce_gram_buffers(buffers, arenas, calls, rows, group=None):
+    """Sum Gram buffers over the ranks of `group`: one all-reduce per flat arena (normally exactly one)
+    plus one per buffer that lives outside the arenas, then the per-name call / row counters, so every
+    rank ends up with the same keys.  Works on any backend (NCCL on the GPUs, gloo in the CPU tests)."""
+    import torch.distributed as dist
+
+    for arena in arenas:
+        dist.all_reduce(arena, op=dist.ReduceOp.SUM, group=group)
+    spans = [(a.data_ptr(), a.data_ptr() + a.numel() * a.element_size()) for a in arenas]
+    names = sorted(buffers)
+    for name in names:
+        g = buffers[name]
+        if not any(lo <= g.data_ptr() < hi for lo, hi in spans):
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+    if names:
+        dev = buffers[names[0]].device
+        counts = torch.tensor([[calls[n], rows[n]] for n in names], dtype=torch.int64, device=dev)
+        dist.all_reduce(counts, group=group)
+        for n, (c, r) in zip(names, counts.tolist()):
+            calls[n], rows[n] = c, r
+
+
+class GramCache:
+    """Accumulates G[name] += X^T X for every hooked module call, on the GPU, in fp32.
+
+    All buffers of the modules known at register() time live in one flat arena, so the data-parallel
+    reduction is a single all-reduce and the buffers never move.  Modules whose width is only known
+    at their first call get individual buffers.
+    """
+
+    def __init__(self, device=None, use_simt=False):
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.type != "cuda":
+            raise RuntimeError("GramCache needs a CUDA device: the Gram hot path has no CPU fallback")
+        self._lib = _lib.lib()
+        self._fn = self._lib.vlm_syrk_accum_simt if use_simt else self._lib.vlm_syrk_accum
+        self.buffers = {}       # name -> fp32 [d, d] (upper triangle authoritative until finalize())
+        self._arenas = []      # flat fp32 arenas the registered buffers are views of
+        self.calls = defaultdict(int)
+        self.rows = defaultdict(int)
+        self._handles = []
+        self._finalized = True
+
+    # ---- the hook -------------------------------------------------------------------------------
+    def hook_gram_input(self, module, input, output):
+        """Forward hook: same contract as the reference closure (cache_gram_matrices.py:246-254)."""
+        if isinstance(input, tuple):
+            input = input[0]
+        self.accumulate(module.module_name, input)
+
+    __call__ = hook_gram_input
+
+    def accumulate(self, name, x):
+        d = x.shape[-1]
+        if x.device != self.device:
+            raise RuntimeError(f"activation for {name} is on {x.device}, GramCache is on {self.device}")
+        x = x.detach()
+        if x.dtype not in _DTYPES:
+            x = x.float()
+        x2 = x.reshape(-1, d)
+        if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) < d):
+            x2 = x2.contiguous()
+        elem = x2.element_size()
+        ldx = x2.stride(0) if x2.shape[0] > 1 else d
+        fn = self._fn
+        if (x2.data_ptr() % 16) or ((ldx * elem) % 16):
+            fn = self._lib.vlm_syrk_accum_simt  # TMA cannot address it; CUDA-core kernel, same contract
+        g = self.buffers.get(name)
+        if g is None:
+            g = self.buffers[name] = torch.zeros(d, d, dtype=torch.float32, device=self.device)
+        elif g.shape[0] != d:
+            raise RuntimeError(f"{name}: activation width changed from {g.shape[0]} to {d}")
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(fn(x2.data_ptr(), _DTYPES[x2.dtype], x2.shape[0], d, ldx, g.data_ptr(), g.stride(0), stream))
+        self.calls[name] += 1
+        self.rows[name] += x2.shape[0]
+        self._finalized = False
+
+    # ---- registration ---------------------------------------------------------------------------
+    def register(self, model, use_moe=True, all_keys=None):
+        """The reference's selection rule (cache_gram_matrices.py:278-281): every module whose
+        qualified name ends with one of all_keys and does not contain '.bias'.  Sets
+        module.module_name and registers the hook; returns the list of hooked names."""
+        picked = []
+        for name, module in select_hooked_modules(model, use_moe, all_keys):
+            module.module_name = name
+            self._handles.append(module.register_forward_hook(self.hook_gram_input))
+            picked.append((name, _in_features(module)))
+        self._allocate_arena([(n, d) for n, d in picked if d is not None and n not in self.buffers])
+        return [n for n, _ in picked]
+
+    def _allocate_arena(self, named_dims):
+        if not named_dims:
+            return
+        total = sum(d * d for _, d in named_dims)
+        arena = torch.zeros(total, dtype=torch.float32, device=self.device)
+        off = 0
+        for name, d in named_dims:
+            self.buffers[name] = arena[off: off + d * d].view(d, d)
+            off += d * d
+        self._arenas.append(arena)
+
+    def remove_hooks(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+    # ---- results --------------------------------------------------------------------------------
+    def live_names(self):
+        """Names whose hook fired at least once (ModuleDicts and unused experts never do)."""
+        return [n for n in self.buffers if self.calls[n] > 0]
+
+    def all_reduce(self, group=None):
+        """Data-parallel calibration: sum the per-rank Gram buffers (NCCL all-reduce over NVLink).
+        The reference has no such step (every DDP rank writes its own file)."""
+        reduce_gram_buffers(self.buffers, self._arenas, self.calls, self.rows, group)
+
+    def finalize(self):
+        """Mirror the upper triangles into the lower ones (after the last accumulate / all_reduce)."""
+        if self._finalized:
+            return
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        for name in self.live_names():
+            g = self.buffers[name]
+            _lib.check(self._lib.vlm_sym_finalize(g.data_ptr(), g.shape[0], g.stride(0), None, 0, stream))
+        self._finalized = True
+
+    def gram(self, name):
+        """Full symmetric fp32 Gram of one module, on the device."""
+        self.finalize()
+        return self.buffers[name]
+
+    def state_dict(self, dtype=torch.float64, device="cpu"):
+        """{module_name: (d,d) tensor} for every module that fired — by default fp64 CPU tensors, the
+        format of the reference's Gram file, in the reference's insertion order (first-call order
+        there; registration order here, which is the same for a sequential forward)."""
+        self.finalize()
+        out = defaultdict(float)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        for name in self.live_names():
+            g = self.buffers[name]
+            if dtype == torch.float64:
+                wide = torch.empty(g.shape, dtype=torch.float64, device=self.device)
+                _lib.check(self._lib.vlm_sym_finalize(g.data_ptr(), g.shape[0], g.stride(0), wide.data_ptr(),
+                                                      wide.stride(0), stream))
+                out[name] = wide.to(device)
+            else:
+                out[name] = g.to(device=device, dtype=dtype)
+        return out
+
+    def save(self, path):
+        """torch.save of the reference-format dict (src/cache_gram_matrices.py:349)."""
+        torch.save(self.state_dict(), path)
+
+    def reset(self):
+        for g in self.buffers.values():
+            g.zero_()
+        self.calls.clear()
+        self.rows.clear()
+        self._finalized = True
+
+
+def hook_gram_input_factory(cache):
+    """For code that wants a bare function like the reference's closure."""
+
+    def hook_gram_input(module, input, output):
+        cache.hook_gram_input(module, input, output)
+
+    return hook_gram_input

@@ -1,0 +1,353 @@
+"""merge.py — the three merge methods of ViLTransformerSS as state_dict -> state_dict functions on the
+B200: merge_weights (src/vilt/modules/vilt_module.py:533-638), sum_task_vectors (:640-746) and
+regmean (:366-531).  Same names, same config keys, same key layout of the result, same dtypes
+(fp32, and fp64 for RegMean's linear weights); the arithmetic runs in libvlmerge:
+
+  * every elementwise target of a call goes through ONE vlm_merge_plan launch (kernel (b));
+  * RegMean's W*Ghat / sum Ghat / solve run per linear through vlm_regmean_rhs,
+    vlm_gram_scale_accum and vlm_spd_solve_right (kernel (c) + cuSOLVER).
+
+Inputs may live on the CPU (the reference's case: torch.load(map_location="cpu")) or already on the
+GPU.  CPU inputs are staged into one device arena and the result comes back in one pinned buffer;
+GPU inputs are used in place and the result stays on the GPU.  With a process group, targets are
+sharded by tensor over the ranks and the merged tensors are all-gathered at the end.
+"""
+import ctypes
+import time
+from types import SimpleNamespace
+
+import torch
+
+from . import _lib
+from .plan import MEAN, SEQ_LERP, WSUM, is_passthrough_key, plan_merge_weights, plan_regmean, plan_sum_task_vectors
+
+_ALIGN = 4  # elements: keeps every arena segment 16-byte aligned for the 128-bit path
+
+
+def _round_up(n, a=_ALIGN):
+    return (n + a - 1) // a * a
+
+
+def _load(path):
+    """torch.load for the reference's pickled artefacts (PL checkpoints, defaultdict Gram files)."""
+    return torch.load(path, map_location="cpu", weights_only=False)
+
+
+def _resolve_device(state_dict, device):
+    if device is not None:
+        return torch.device(device)
+    for v in state_dict.values():
+        if torch.is_tensor(v) and v.is_cuda:
+            return v.device
+    if not torch.cuda.is_available():
+        raise RuntimeError("the merge hot path runs on a CUDA device only (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _shard(ops, cost, world):
+    """Greedy size-balanced assignment of ops to ranks (largest first); deterministic on every rank."""
+    owner = {}
+    load = [0] * world
+    for idx in sorted(range(len(ops)), key=lambda i: (-cost(ops[i]), i)):
+        r = min(range(world), key=lambda k: (load[k], k))
+        owner[idx] = r
+        load[r] += cost(ops[idx])
+    return owner
+
+
+class ShardLayout:
+    """Tensor-sharded placement of merge targets over `world` ranks and the flat layout of the
+    all-gathered result.  Pure Python: every rank derives the same layout from (sizes, world), so the
+    only thing that travels is one all_gather_into_tensor of equal-width shards."""
+
+    def __init__(self, sizes, world, cost=None, align=_ALIGN):
+        self.sizes, self.world = list(sizes), world
+        idx = list(range(len(self.sizes)))
+        cost = cost or (lambda i: self.sizes[i])
+        self.owner = _shard(idx, cost, world) if world > 1 else {i: 0 for i in idx}
+        self.offset, self.shard_size = {}, [0] * world
+        for i in idx:
+            r = self.owner[i]
+            self.offset[i] = self.shard_size[r]
+            self.shard_size[r] += _round_up(self.sizes[i], align)
+        self.width = max(self.shard_size + [1])
+
+    def mine(self, rank):
+        return [i for i in range(len(self.sizes)) if self.owner[i] == rank]
+
+    def gather(self, local, rank, group):
+        """local: flat tensor holding this rank's shard (>= shard_size[rank] elements).  Returns the
+        flat tensor [world * width] with every rank's shard."""
+        import torch.distributed as dist
+
+        if self.world == 1:
+            return local
+        padded = torch.zeros(self.width, dtype=local.dtype, device=local.device)
+        padded[: self.shard_size[rank]].copy_(local[: self.shard_size[rank]])
+        out = torch.empty(self.world * self.width, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, padded, group=group)
+        return out
+
+    def view(self, full, i, shape):
+        base = (self.owner[i] * self.width if self.world > 1 else 0) + self.offset[i]
+        return full[base: base + self.sizes[i]].view(shape)
+
+
+def _run_elementwise(ops, lookup, shapes, device, out_device, group=None, stats=None):
+    """Executes the WSUM / SEQ_LERP / MEAN ops in one kernel launch (per rank).
+    lookup(op, j) -> source tensor j of op; shapes[dst] -> torch.Size.  Returns {dst: fp32 tensor}."""
+    import torch.distributed as dist
+
+    lib = _lib.lib()
+    world = dist.get_world_size(group) if group is not None else 1
+    rank = dist.get_rank(group) if group is not None else 0
+    numel = {op.dst: int(torch.Size(shapes[op.dst]).numel()) for op in ops}
+    layout = ShardLayout([numel[op.dst] for op in ops], world)
+    out_off, shard_size = layout.offset, layout.shard_size
+    mine = layout.mine(rank)
+
+    # input arena for sources that are not already usable in place
+    def in_place(t):
+        return t.is_cuda and t.device == device and t.dtype == torch.float32 and t.is_contiguous()
+
+    staged, in_total = [], 0
+    for i in mine:
+        for j in range(len(ops[i].srcs) + (1 if ops[i].central else 0)):
+            t = lookup(ops[i], j)
+            if tuple(t.shape) != tuple(shapes[ops[i].dst]):
+                raise RuntimeError(f"{ops[i].dst}: source {j} has shape {tuple(t.shape)}, expected {tuple(shapes[ops[i].dst])}")
+            if not in_place(t):
+                staged.append((i, j, in_total, t))
+                in_total += _round_up(t.numel())
+    arena_in = torch.empty(max(in_total, 1), dtype=torch.float32, device=device)
+    h2d = 0
+    for _, _, off, t in staged:
+        src = t.detach().reshape(-1)
+        if src.dtype != torch.float32:
+            src = src.float()
+        arena_in[off: off + src.numel()].copy_(src, non_blocking=True)
+        h2d += src.numel() * 4 if not t.is_cuda else 0
+    staged_at = {(i, j): off for i, j, off, _ in staged}
+
+    arena_out = torch.empty(max(shard_size[rank], 1), dtype=torch.float32, device=device)
+    segs = (_lib.MergeSeg * max(len(mine), 1))()
+    keep = []
+    for s, i in enumerate(mine):
+        op = ops[i]
+        n_src = len(op.srcs) + (1 if op.central else 0)
+        if n_src > _lib.MERGE_MAX_SRC:
+            raise RuntimeError(f"{op.dst}: {n_src} sources exceed VLM_MERGE_MAX_SRC")
+        seg = segs[s]
+        seg.dst = arena_out.data_ptr() + out_off[i] * 4
+        for j in range(n_src):
+            if (i, j) in staged_at:
+                seg.src[j] = arena_in.data_ptr() + staged_at[(i, j)] * 4
+            else:
+                t = lookup(op, j)
+                keep.append(t)
+                seg.src[j] = t.data_ptr()
+        coefs = ([0.0] if op.central else []) + list(op.coefs)
+        for j, c in enumerate(coefs):
+            seg.coef[j] = c
+        seg.n = numel[op.dst]
+        seg.n_src = n_src
+        seg.mode = op.mode
+    stream = torch.cuda.current_stream(device).cuda_stream
+    if mine:
+        plan = ctypes.c_void_p()
+        _lib.check(lib.vlm_merge_plan_create(segs, len(mine), ctypes.byref(plan)))
+        try:
+            _lib.check(lib.vlm_merge_plan_run(plan, stream))
+            if stats is not None:
+                stats["merge_bytes"] = stats.get("merge_bytes", 0) + int(lib.vlm_merge_plan_bytes(plan))
+        finally:
+            torch.cuda.current_stream(device).synchronize()
+            lib.vlm_merge_plan_destroy(plan)
+
+    # all-gather of the merged shards (the path's one exchange step)
+    full = layout.gather(arena_out, rank, group)
+    if out_device.type == "cpu":
+        host = torch.empty(full.numel(), dtype=torch.float32, pin_memory=True)
+        host.copy_(full, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+        full = host
+        if stats is not None:
+            stats["d2h_bytes"] = stats.get("d2h_bytes", 0) + full.numel() * 4
+    if stats is not None:
+        stats["h2d_bytes"] = stats.get("h2d_bytes", 0) + h2d
+    out = {op.dst: layout.view(full, i, shapes[op.dst]) for i, op in enumerate(ops)}
+    return out
+
+
+def _assemble(state_dict, ops, computed):
+    """Result dict in the reference's order: pass-through keys first, then the 13 targets per layer."""
+    new = {k: v for k, v in state_dict.items() if is_passthrough_key(k)}
+    for op in ops:
+        new[op.dst] = state_dict[op.passthrough] if op.passthrough else computed[op.dst]
+    return new
+
+
+def _out_device(state_dict, ops):
+    for op in ops:
+        for k in op.srcs:
+            return state_dict[k].device
+        if op.regmean:
+            return state_dict[op.regmean[0][0]].device
+    return torch.device("cpu")
+
+
+def merge_weights(state_dict, config, device=None, num_layers=12, group=None, stats=None):
+    """Interpolation merge.  config keys: merge_ratio, only_activate_used_experts,
+    vlffn_start_layer_index, loss_names (src/vilt/config.py:141-149)."""
+    device = _resolve_device(state_dict, device)
+    ops = plan_merge_weights(state_dict.keys(), config, num_layers)
+    todo = [op for op in ops if not op.passthrough]
+    shapes = {op.dst: state_dict[op.srcs[0]].shape for op in todo}
+    with torch.cuda.device(device):
+        computed = _run_elementwise(todo, lambda op, j: state_dict[op.srcs[j]], shapes, device,
+                                    _out_device(state_dict, todo), group, stats)
+    return _assemble(state_dict, ops, computed)
+
+
+def sum_task_vectors(state_dict, config, device=None, num_layers=12, group=None, stats=None, central_weight=None):
+    """Modality arithmetic with the reference's sequential semantics.  The centre is
+    config['central_weight'] (a checkpoint path, as in the reference) unless a dict is passed.  Unlike the
+    reference, the loaded centre is not mutated."""
+    device = _resolve_device(state_dict, device)
+    central = central_weight if central_weight is not None else _load(config["central_weight"])
+    if "state_dict" in central:
+        central = central["state_dict"]
+    ops = plan_sum_task_vectors(state_dict.keys(), central.keys(), config, num_layers)
+    todo = [op for op in ops if not op.passthrough]
+    shapes = {op.dst: central[op.dst].shape for op in todo}
+
+    def lookup(op, j):
+        return central[op.dst] if j == 0 else state_dict[op.srcs[j - 1]]
+
+    with torch.cuda.device(device):
+        computed = _run_elementwise(todo, lookup, shapes, device, _out_device(state_dict, todo), group, stats)
+    return _assemble(state_dict, ops, computed)
+
+
+def _as_gram_dict(grams):
+    if hasattr(grams, "state_dict") and hasattr(grams, "buffers"):  # a GramCache: stay on the device, fp32
+        grams.finalize()
+        return {n: grams.buffers[n] for n in grams.live_names()}
+    return grams
+
+
+def regmean(state_dict, config, device=None, num_layers=12, group=None, stats=None, gram_matrices=None):
+    """RegMean merge.  config keys: gram_matrices (path of the Gram file, as in the reference — or pass
+    gram_matrices= a dict / GramCache), scaling_for_non_diag, vlffn_start_layer_index, loss_names.
+    Linear weights come back fp64 like the reference's; biases / LayerNorms fp32."""
+    import torch.distributed as dist
+
+    device = _resolve_device(state_dict, device)
+    lib = _lib.lib()
+    grams = _as_gram_dict(gram_matrices if gram_matrices is not None else _load(config["gram_matrices"]))
+    alpha = float(config["scaling_for_non_diag"])
+    ops = plan_regmean(state_dict.keys(), grams.keys(), config, num_layers)
+    todo = [op for op in ops if not op.passthrough]
+    mean_ops = [op for op in todo if op.regmean is None]
+    lin_ops = [op for op in todo if op.regmean is not None]
+    out_device = _out_device(state_dict, todo)
+    with torch.cuda.device(device):
+        shapes = {op.dst: state_dict[op.srcs[0]].shape for op in mean_ops}
+        computed = _run_elementwise(mean_ops, lambda op, j: state_dict[op.srcs[j]], shapes, device, out_device,
+                                    group, stats)
+
+        world = dist.get_world_size(group) if group is not None else 1
+        rank = dist.get_rank(group) if group is not None else 0
+
+        def cost(op):
+            o, i = state_dict[op.regmean[0][0]].shape
+            return i * i * i // 3 + 2 * len(op.regmean) * o * i * i + 2 * o * i * i
+
+        lin_sizes = [int(state_dict[op.regmean[0][0]].numel()) for op in lin_ops]
+        lin_layout = ShardLayout(lin_sizes, world, cost=lambda i: cost(lin_ops[i]), align=1)
+        owner = lin_layout.owner
+        stream = torch.cuda.current_stream(device).cuda_stream
+        results = {}
+        t_rhs = t_solve = 0.0
+        for idx, op in enumerate(lin_ops):
+            if owner[idx] != rank:
+                continue
+            out_f, in_f = state_dict[op.regmean[0][0]].shape
+            acc = torch.empty(out_f, in_f, dtype=torch.float64, device=device)
+            summed = torch.empty(in_f, in_f, dtype=torch.float64, device=device)
+            t0 = time.perf_counter() if stats is not None else 0.0
+            for n, (wkey, gkey) in enumerate(op.regmean):
+                w = state_dict[wkey].detach().to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+                g = grams[gkey]
+                if g.dtype not in (torch.float64, torch.float32):
+                    g = g.double()
+                g = g.detach().to(device=device, non_blocking=True).contiguous()
+                if tuple(g.shape) != (in_f, in_f):
+                    raise RuntimeError(f"Gram {gkey} has shape {tuple(g.shape)}, expected {(in_f, in_f)}")
+                gdt = _lib.VLM_F64 if g.dtype == torch.float64 else _lib.VLM_F32
+                _lib.check(lib.vlm_gram_scale_accum(g.data_ptr(), gdt, in_f, g.stride(0), alpha, summed.data_ptr(),
+                                                    summed.stride(0), int(n > 0), stream))
+                _lib.check(lib.vlm_regmean_rhs(w.data_ptr(), out_f, in_f, w.stride(0), g.data_ptr(), gdt, g.stride(0),
+                                               alpha, acc.data_ptr(), acc.stride(0), int(n > 0), stream))
+            if stats is not None:
+                torch.cuda.current_stream(device).synchronize()
+                t1 = time.perf_counter()
+                t_rhs += t1 - t0
+            try:
+                _lib.check(lib.vlm_spd_solve_right(summed.data_ptr(), in_f, summed.stride(0), acc.data_ptr(), out_f,
+                                                   acc.stride(0), stream))
+            except _lib.VlmError as e:
+                if e.code == _lib.ERR_NOT_SPD:  # the reference's torch.inverse raises on a singular sum too
+                    raise torch.linalg.LinAlgError(f"{op.dst}: {e}") from e
+                raise
+            if stats is not None:
+                t_solve += time.perf_counter() - t1
+            results[op.dst] = acc
+        if stats is not None:
+            stats["rhs_seconds"] = stats.get("rhs_seconds", 0.0) + t_rhs
+            stats["solve_seconds"] = stats.get("solve_seconds", 0.0) + t_solve
+
+        if world > 1:  # all-gather the solved weights: flat fp64, every rank knows every size
+            local = torch.zeros(lin_layout.width, dtype=torch.float64, device=device)
+            for idx in lin_layout.mine(rank):
+                r = results[lin_ops[idx].dst]
+                local[lin_layout.offset[idx]: lin_layout.offset[idx] + r.numel()].copy_(r.reshape(-1))
+            gathered = lin_layout.gather(local, rank, group)
+            for idx, op in enumerate(lin_ops):
+                results[op.dst] = lin_layout.view(gathered, idx, state_dict[op.regmean[0][0]].shape)
+        for op in lin_ops:
+            computed[op.dst] = results[op.dst].to(out_device)
+    return _assemble(state_dict, ops, computed)
+
+
+class Merger:
+    """Object form with the reference's calling convention: methods read self.hparams.config[...]
+    (vilt_module.py:389,397,557,576,660...).  `ViLTransformerSS.merge_weights = Merger.merge_weights`
+    style patching, or Merger(config).regmean(state_dict)."""
+
+    def __init__(self, config, num_layers=12, device=None, group=None):
+        self.hparams = SimpleNamespace(config=config)
+        self.num_layers, self.device, self.group = num_layers, device, group
+
+    def merge_weights(self, state_dict):
+        return merge_weights(state_dict, self.hparams.config, self.device, self.num_layers, self.group)
+
+    def sum_task_vectors(self, state_dict):
+        return sum_task_vectors(state_dict, self.hparams.config, self.device, self.num_layers, self.group)
+
+    def regmean(self, state_dict):
+        return regmean(state_dict, self.hparams.config, self.device, self.num_layers, self.group)
+
+    def apply(self, state_dict):
+        """The load-time dispatch of vilt_module.py:284-291."""
+        cfg = self.hparams.config
+        if cfg.get("merge_weights"):
+            return self.merge_weights(state_dict)
+        if cfg.get("sum_task_vectors"):
+            return self.sum_task_vectors(state_dict)
+        if cfg.get("regmean"):
+            return self.regmean(state_dict)
+        return state_dict
+
+
+__all__ = ["merge_weights", "sum_task_vectors", "regmean", "Merger", "WSUM", "SEQ_LERP", "MEAN"]
