@@ -30,20 +30,43 @@ def setup():
 
 
 def test_gram_caching_matches_reference_hooks(setup):
+    """Against the golden summaries of the reference's own hooks (reference forward on CPU): diagonal,
+    Frobenius norm and trace have no cancellation, so the 1e-3 Gram tolerance applies to them directly; the
+    row sums do cancel, so they get the Cauchy-Schwarz form of the same bound; one Gram is compared in full."""
     z, meta, cfg, model, cache = setup
     grams = cache.state_dict()
     assert sorted(grams.keys()) == sorted(meta["gram_keys"]) and len(grams) == 96
-    worst = 0.0
     for k in meta["gram_keys"]:
         g = grams[k].numpy()
         fro, trace = z[f"gram/{k}/fro_trace"]
-        for got, want in ((np.diag(g), z[f"gram/{k}/diag"]), (g.sum(1), z[f"gram/{k}/rowsum"])):
-            worst = max(worst, np.linalg.norm(got - want) / np.linalg.norm(want))
-        worst = max(worst, abs(np.linalg.norm(g) - fro) / fro, abs(np.trace(g) - trace) / trace)
-    assert worst < 1e-3, worst
+        assert np.linalg.norm(np.diag(g) - z[f"gram/{k}/diag"]) < 1e-3 * np.linalg.norm(z[f"gram/{k}/diag"]), k
+        assert abs(np.linalg.norm(g) - fro) < 1e-3 * fro and abs(np.trace(g) - trace) < 1e-3 * trace, k
+        assert np.linalg.norm(g.sum(1) - z[f"gram/{k}/rowsum"]) < 1e-3 * fro * np.sqrt(g.shape[0]), k
     k = "transformer.blocks.0.attn.v"
     full = z[f"gram_full/{k}"]
     assert np.linalg.norm(grams[k].numpy() - full) / np.linalg.norm(full) < 1e-3
+
+
+def test_gram_caching_matches_fp64_hook_on_identical_activations(setup):
+    """The reference hook's arithmetic (fp64 X^T X, accumulated) on the very activations our hook saw:
+    all 96 Grams in full, relative Frobenius error <= 1e-3 (BASELINE.json)."""
+    z, meta, cfg, model, cache = setup
+    ref = {}
+    mods = dict(model.named_modules())
+    handles = []
+    for name in meta["gram_keys"]:
+        def probe(m, i, o, name=name):
+            x = (i[0] if isinstance(i, tuple) else i).double()
+            x = x.reshape(-1, x.shape[-1])
+            ref[name] = ref.get(name, 0) + x.T @ x
+        handles.append(mods[name].register_forward_hook(probe))
+    with torch.no_grad():
+        for bs, seed, pad in meta["calib_batches"]:
+            model(vlm.synthetic_batch(bs, cfg, seed=seed, pad=pad, device="cuda"))
+    for h in handles:
+        h.remove()
+    worst = max(((cache.gram(k).double() - ref[k]).norm() / ref[k].norm()).item() for k in meta["gram_keys"])
+    assert worst < 1e-3, worst
 
 
 @pytest.mark.parametrize("vname", ["interp", "arith", "regmean"])

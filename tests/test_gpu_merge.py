@@ -15,7 +15,7 @@ G = MergeGolden()
 
 
 def _t(d, device="cpu"):
-    return {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in d.items()}
+    return {k: torch.from_numpy(np.array(v)).to(device) for k, v in d.items()}  # np.array keeps 0-dim shapes
 
 
 def _run(vname, device_inputs):

@@ -37,20 +37,20 @@ def test_schedule_covers_upper_triangle_once(rows, d, elem):
             assert blk not in blocks
             blocks.add(blk)
     assert blocks == {(i, j) for i in range(nb) for j in range(i, nb)}
-    npanels = (kc + 63) // 64
+    npanels = (kc + 255) // 256
     assert max(costs) - min(costs) <= 4 * npanels  # equal shares per panel up to one wide chunk
 
 
 def test_rows_are_swept_panel_major():
-    """All CTAs work on the same 64-chunk row panel at the same step of their lists (L2 locality), and
+    """All CTAs work on the same 256-chunk row panel at the same step of their lists (L2 locality), and
     no accumulation runs across a panel boundary."""
     segs, off = vlm._lib.syrk_schedule(36928, 3072, 4, 148)
     for c in range(len(off) - 1):
         mine = segs[off[c]: off[c + 1]]
-        panels = [s[3] // 64 for s in mine]
-        assert panels == sorted(panels)                       # panel by panel
-        assert set(panels) == set(range((1154 + 63) // 64))   # every CTA takes part in every panel
-        assert all(s[3] // 64 == (s[4] - 1) // 64 for s in mine)
+        panels = [s[3] // 256 for s in mine]
+        assert panels == sorted(panels)                         # panel by panel
+        assert set(panels) == set(range((1154 + 255) // 256))   # every CTA takes part in every panel
+        assert all(s[3] // 256 == (s[4] - 1) // 256 for s in mine)
 
 
 def test_small_problems_use_fewer_ctas():

@@ -375,6 +375,14 @@ static void regmean_case(int out_f, int in_f, double alpha) {
 
 int main(int argc, char** argv) {
   const bool full = argc > 1 && !strcmp(argv[1], "full");
+  if (argc >= 6 && !strcmp(argv[1], "case")) {  // selftest case <f32|bf16|f16> <rows> <d> <iters> [positive]
+    const int64_t rows = atoll(argv[3]);
+    const int d = atoi(argv[4]), iters = atoi(argv[5]), mode = argc > 6 ? atoi(argv[6]) : 0;
+    if (!strcmp(argv[2], "f32")) syrk_case<float>("case f32", VLM_F32, rows, d, mode, false, iters, 2e-3);
+    else if (!strcmp(argv[2], "bf16")) syrk_case<__nv_bfloat16>("case bf16", VLM_BF16, rows, d, mode, false, iters, 1e-4);
+    else syrk_case<__half>("case f16", VLM_F16, rows, d, mode, false, iters, 1e-4);
+    return g_fail;
+  }
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   printf("device: %s, %d SMs, cc %d.%d, vlm abi %d\n", prop.name, prop.multiProcessorCount, prop.major, prop.minor,

@@ -319,7 +319,7 @@ int launch_kernel(int dev, const DeviceSchedule& sched, const CUtensorMap& tm_x,
 // which bounds the tensor core's truncating fp32 accumulation (the cross-panel sum is the
 // round-to-nearest fp32 reduce-add into G).
 void build_syrk_schedule(int64_t kc, int d, int nsm, std::vector<SyrkSeg>* segs, std::vector<int>* off) {
-  int64_t panel_chunks = 64;  // 2048 fp32 rows / 4096 16-bit rows per panel
+  int64_t panel_chunks = 256;  // 8192 fp32 rows / 16384 16-bit rows per panel (swept on the B200: 32..512)
   if (const char* e = getenv("VLM_SYRK_PANEL_CHUNKS")) panel_chunks = std::max(1, atoi(e));
   const int nb = (d + 127) / 128;
   struct Tile {

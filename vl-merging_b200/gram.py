@@ -87,6 +87,8 @@ class GramCache:
         self.device = torch.device(device if device is not None else "cuda")
         if self.device.type != "cuda":
             raise RuntimeError("GramCache needs a CUDA device: the Gram hot path has no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self._lib = _lib.lib()
         self._fn = self._lib.vlm_syrk_accum_simt if use_simt else self._lib.vlm_syrk_accum
         self.buffers = {}       # name -> fp32 [d, d] (upper triangle authoritative until finalize())

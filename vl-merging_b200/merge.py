@@ -35,7 +35,10 @@ def _load(path):
 
 def _resolve_device(state_dict, device):
     if device is not None:
-        return torch.device(device)
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        return device
     for v in state_dict.values():
         if torch.is_tensor(v) and v.is_cuda:
             return v.device
