@@ -75,6 +75,11 @@ int vlm_sym_finalize(float* g, int d, int64_t ldg, double* out_f64, int64_t ld64
 int vlm_syrk_schedule_host(int64_t rows, int d, int elem_bytes, int nsm, int32_t* segs_out, int cap,
                            int32_t* off_out, int off_cap, int* ncta_out);
 
+/* Same for the CTA-pair kernel (the default when d is a whole number of 128-byte column groups): 4 int32 per
+ * segment {super_row, super_col (256-column units), chunk_begin, chunk_end} and ncluster+1 offsets. */
+int vlm_syrk_pair_schedule_host(int64_t rows, int d, int elem_bytes, int nsm, int32_t* segs_out, int cap,
+                                int32_t* off_out, int off_cap, int* ncluster_out);
+
 /* ---- (b) streaming merge -------------------------------------------------------------------
  * Replaces the per-tensor loops of merge_weights (src/vilt/modules/vilt_module.py:586-635),
  * sum_task_vectors (:696-744) and the simple-average branches of regmean (:436-457, :486-529).

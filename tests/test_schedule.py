@@ -37,20 +37,22 @@ def test_schedule_covers_upper_triangle_once(rows, d, elem):
             assert blk not in blocks
             blocks.add(blk)
     assert blocks == {(i, j) for i in range(nb) for j in range(i, nb)}
-    npanels = (kc + 255) // 256
+    pc = max(32, int(40e6 / (128.0 * d)))
+    npanels = (kc + pc - 1) // pc
     assert max(costs) - min(costs) <= 4 * npanels  # equal shares per panel up to one wide chunk
 
 
 def test_rows_are_swept_panel_major():
-    """All CTAs work on the same 256-chunk row panel at the same step of their lists (L2 locality), and
+    """All CTAs work on the same ~40 MB row panel at the same step of their lists (L2 locality), and
     no accumulation runs across a panel boundary."""
     segs, off = vlm._lib.syrk_schedule(36928, 3072, 4, 148)
     for c in range(len(off) - 1):
         mine = segs[off[c]: off[c + 1]]
-        panels = [s[3] // 256 for s in mine]
-        assert panels == sorted(panels)                         # panel by panel
-        assert set(panels) == set(range((1154 + 255) // 256))   # every CTA takes part in every panel
-        assert all(s[3] // 256 == (s[4] - 1) // 256 for s in mine)
+        pc = int(40e6 / (128.0 * 3072))                       # ~40 MB of X per panel
+        panels = [s[3] // pc for s in mine]
+        assert panels == sorted(panels)                       # panel by panel
+        assert set(panels) == set(range((1154 + pc - 1) // pc))  # every CTA takes part in every panel
+        assert all(s[3] // pc == (s[4] - 1) // pc for s in mine)
 
 
 def test_small_problems_use_fewer_ctas():
@@ -58,3 +60,26 @@ def test_small_problems_use_fewer_ctas():
     assert len(off) - 1 == 1
     _, off = vlm._lib.syrk_schedule(2560, 768, 4, 148)
     assert len(off) - 1 < 148
+
+
+@pytest.mark.parametrize("rows,d,elem", [c for c in CASES if c[1] % (128 // c[2]) == 0])
+def test_pair_schedule_covers_super_tiles_once(rows, d, elem):
+    """CTA-pair kernel: every (super-tile, chunk) exactly once, b >= a, equal shares per cluster and panel."""
+    segs, off = vlm._lib.syrk_pair_schedule(rows, d, elem, 148)
+    kc = (rows + 128 // elem - 1) // (128 // elem)
+    nsb = (d + 255) // 256
+    assert off[0] == 0 and off[-1] == len(segs) and 1 <= len(off) - 1 <= 74
+    cover = defaultdict(list)
+    costs = []
+    for c in range(len(off) - 1):
+        mine = segs[off[c]: off[c + 1]]
+        costs.append(sum(k1 - k0 for _, _, k0, k1 in mine))
+        for a, b, k0, k1 in mine:
+            assert 0 <= a <= b < nsb and 0 <= k0 < k1 <= kc
+            cover[(a, b)].append((k0, k1))
+    assert set(cover) == {(a, b) for a in range(nsb) for b in range(a, nsb)}
+    for ivs in cover.values():
+        ivs.sort()
+        assert ivs[0][0] == 0 and ivs[-1][1] == kc and all(x[1] == y[0] for x, y in zip(ivs, ivs[1:]))
+    pc = max(32, int(40e6 / (128.0 * d)))
+    assert max(costs) - min(costs) <= 2 * ((kc + pc - 1) // pc)

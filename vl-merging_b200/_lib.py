@@ -45,6 +45,8 @@ SIGNATURES = {
     "vlm_sym_finalize": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p]),
     "vlm_syrk_schedule_host": (c_int, [c_int64, c_int, c_int, c_int, POINTER(c_int32), c_int, POINTER(c_int32),
                                        c_int, POINTER(c_int)]),
+    "vlm_syrk_pair_schedule_host": (c_int, [c_int64, c_int, c_int, c_int, POINTER(c_int32), c_int, POINTER(c_int32),
+                                            c_int, POINTER(c_int)]),
     "vlm_merge_plan_create": (c_int, [POINTER(MergeSeg), c_int, POINTER(c_void_p)]),
     "vlm_merge_plan_run": (c_int, [c_void_p, c_void_p]),
     "vlm_merge_plan_destroy": (c_int, [c_void_p]),
@@ -107,3 +109,15 @@ def syrk_schedule(rows, d, elem_bytes=4, nsm=148):
     if n < 0:
         check(n)
     return [tuple(segs[5 * i: 5 * i + 5]) for i in range(n)], list(off[: ncta.value + 1])
+
+
+def syrk_pair_schedule(rows, d, elem_bytes=4, nsm=148):
+    """Host-side view of the CTA-pair SYRK decomposition: (list of (super_row, super_col, k0, k1), offsets)."""
+    cap = 1 << 16
+    segs = (c_int32 * (4 * cap))()
+    off = (c_int32 * (nsm + 2))()
+    ncl = c_int(0)
+    n = lib().vlm_syrk_pair_schedule_host(rows, d, elem_bytes, nsm, segs, cap, off, nsm + 2, ctypes.byref(ncl))
+    if n < 0:
+        check(n)
+    return [tuple(segs[4 * i: 4 * i + 4]) for i in range(n)], list(off[: ncl.value + 1])

@@ -1,6 +1,7 @@
 // api.cu — C-ABI entry points declared in include/vlmerge.h (argument validation, error state) for
 // the Gram path; merge.cu and regmean.cu define their own entry points.
 #include <cstdarg>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -78,6 +79,14 @@ extern "C" int vlm_syrk_accum(const void* x, int dtype, int64_t rows, int d, int
   if (int rc = check_syrk_args("vlm_syrk_accum", x, dtype, rows, d, ldx, g, ldg)) return rc;
   if (rows == 0) return 0;
   if (int rc = require_sm100()) return rc;
+  // VLM_SYRK_VARIANT=1 forces the first-generation (single-CTA) kernel; default is the CTA-pair kernel
+  // whenever the activation has whole 128-byte column groups
+  static const int variant = [] {
+    const char* e = getenv("VLM_SYRK_VARIANT");
+    return e ? atoi(e) : 2;
+  }();
+  if (variant == 2 && syrk_tc2_supported(dtype, d, ldx))
+    return syrk_tc2_launch(x, dtype, rows, d, ldx, g, ldg, static_cast<cudaStream_t>(stream));
   return syrk_tc_launch(x, dtype, rows, d, ldx, g, ldg, static_cast<cudaStream_t>(stream));
 }
 
@@ -117,4 +126,20 @@ extern "C" int vlm_syrk_schedule_host(int64_t rows, int d, int elem_bytes, int n
   }
   for (size_t i = 0; i < off.size(); ++i) off_out[i] = off[i];
   return (int)segs.size();
+}
+
+extern "C" int vlm_syrk_pair_schedule_host(int64_t rows, int d, int elem_bytes, int nsm, int32_t* segs_out, int cap,
+                                           int32_t* off_out, int off_cap, int* ncluster_out) {
+  VLM_REQUIRE(rows > 0 && d > 0 && (elem_bytes == 2 || elem_bytes == 4) && nsm > 1 && ncluster_out, VLM_ERR_INVALID_ARG,
+              "vlm_syrk_pair_schedule_host: bad arguments");
+  const int bk = 128 / elem_bytes;
+  std::vector<int32_t> flat;
+  std::vector<int> off;
+  build_syrk_pair_schedule_host((rows + bk - 1) / bk, d, nsm, &flat, &off);
+  *ncluster_out = (int)off.size() - 1;
+  VLM_REQUIRE((int)flat.size() <= 4 * cap && (int)off.size() <= off_cap, VLM_ERR_INVALID_ARG,
+              "vlm_syrk_pair_schedule_host: output capacity too small (%d segments)", (int)flat.size() / 4);
+  for (size_t i = 0; i < flat.size(); ++i) segs_out[i] = flat[i];
+  for (size_t i = 0; i < off.size(); ++i) off_out[i] = off[i];
+  return (int)flat.size() / 4;
 }

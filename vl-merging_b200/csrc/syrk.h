@@ -1,6 +1,8 @@
 // syrk.h — declarations shared by the SYRK translation units.
 #pragma once
+#include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -13,10 +15,25 @@ struct SyrkSeg {
   int32_t col_a, col_b, w, k0, k1;
 };
 
+// Rows of X are processed in panels small enough to stay in L2 while every tile re-reads them: one chunk
+// (BK rows) of all d columns is always d * 128 bytes, and a panel is ~40 MB of X (VLM_SYRK_PANEL_MB), at
+// least 32 chunks.  VLM_SYRK_PANEL_CHUNKS overrides the result (experiments).
+inline int64_t syrk_panel_chunks(int d) {
+  if (const char* e = getenv("VLM_SYRK_PANEL_CHUNKS")) return std::max(1, atoi(e));
+  double mb = 40.0;
+  if (const char* e = getenv("VLM_SYRK_PANEL_MB")) mb = std::max(1.0, atof(e));
+  return std::max<int64_t>(32, (int64_t)(mb * 1e6 / (128.0 * d)));
+}
+
 void build_syrk_schedule(int64_t kc, int d, int nsm, std::vector<SyrkSeg>* segs, std::vector<int>* off);
 
 int syrk_tc_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,
                    cudaStream_t stream);
+// second generation: CTA pairs + TMA multicast + 3-D boxes (syrk_tc2.cu); needs whole 128-byte column groups
+bool syrk_tc2_supported(int dtype, int d, int64_t ldx);
+int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,
+                    cudaStream_t stream);
+void build_syrk_pair_schedule_host(int64_t kc, int d, int nsm, std::vector<int32_t>* flat, std::vector<int>* off);
 int syrk_simt_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,
                      cudaStream_t stream);
 int sym_finalize_launch(float* g, int d, int64_t ldg, double* out_f64, int64_t ld64, cudaStream_t stream);

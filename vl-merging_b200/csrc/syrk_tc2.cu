@@ -1,0 +1,416 @@
+// syrk_tc2.cu — kernel (a), second generation: CTA pairs with TMA multicast.
+//
+// Same arithmetic and epilogue as syrk_tc.cu (tcgen05.mma kind::tf32 / kind::f16 on MN-major TMA tiles,
+// fp32 accumulators in TMEM, TMA reduce-add into G).  What changes is how bytes reach shared memory,
+// because the first-generation kernel was bound by L2->SM traffic (48 KB per 512 tensor-pipe cycles per
+// SM, issued as 12 small TMA boxes per stage):
+//
+//  * work unit = a 256x256 SUPER-TILE (a, b), b >= a, computed by a cluster of two CTAs: CTA r owns the
+//    row block 2a+r and both column blocks 2b, 2b+1.  The two CTAs need the same B columns, so each
+//    loads ONE B block and multicasts it into both CTAs' shared memory (.multicast::cluster), plus its
+//    own A block: 32 KB from L2 per CTA per stage instead of 48 KB.  On a diagonal super-tile the A
+//    block of CTA r IS B block r: 16 KB per CTA per stage, and CTA 1 only computes its diagonal block
+//    (N = 128) — the block below the diagonal is never formed.
+//  * X is described to TMA as a 3-D tensor {columns-in-group, rows, column groups} (strides 4 B,
+//    pitch, 128 B), so ONE cp.async.bulk.tensor box {128 B, BK rows, groups-per-block} fetches a whole
+//    128-column block in exactly the [group][row][128 B] order the UMMA descriptor wants: 2 TMA
+//    instructions per stage instead of 12.
+//
+// Synchronisation (per CTA): full[s] gets 1 arrival + the bytes of its own A/B loads AND of the peer's
+// multicast half; empty[s] needs 2 arrivals — this CTA's and the peer's tcgen05.commit (multicast
+// commit) — because a slot is overwritten by the peer's multicast as well.  The two CTAs of a cluster
+// walk the same segment list, so they stay in lock-step by construction.
+#include <algorithm>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#include "common.cuh"
+#include "syrk.h"
+#include "umma.cuh"
+
+namespace vlm {
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kStageBytes = 3 * kBlockBytes;  // [B0][B1][A]
+constexpr int kStagingBytes = 16384;
+constexpr int kThreads = 256;
+constexpr int kTmemCols = 512;
+constexpr int kAccCols = 256;
+constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStagingBytes + 256 + 1024;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one box of a 3-D tensor map; lands in this CTA only
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint64_t* bar, void* smem_dst, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// same, delivered to the same smem offset (and signalling the same mbarrier offset) in every CTA of `mask`
+__device__ __forceinline__ void tma_load_3d_mcast(const CUtensorMap* tm, uint64_t* bar, void* smem_dst, int c0,
+                                                  int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5, %6}], [%2], %3;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at this smem offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
+// One unit of work of a CLUSTER: super-tile (sa, sb) in 256-column units, row chunks [k0, k1).
+struct PairSeg {
+  int32_t sa, sb, k0, k1;
+};
+
+template <int ELEM_BYTES, int FMT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
+                const PairSeg* __restrict__ segs, const int* __restrict__ seg_off, int d) {
+  using G = Geo<ELEM_BYTES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint8_t* staging = smem + kStages * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tfull = bars + 2 * kStages;
+  uint64_t* tempty = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 / 1: which row block of the super-tile
+  const int cluster_id = blockIdx.x >> 1;
+  const int seg_begin = seg_off[cluster_id];
+  const int seg_end = seg_off[cluster_id + 1];
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_g);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 2);  // this CTA's MMA commit + the peer's
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barrier inits visible cluster-wide before any multicast lands
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int s = seg_begin; s < seg_end; ++s) {
+      const PairSeg seg = segs[s];
+      const bool diag = seg.sa == seg.sb;
+      const int a_group = (2 * seg.sa + (int)rank) * G::GB;       // first column group of this CTA's A block
+      const int b_group = (2 * seg.sb + (int)rank) * G::GB;       // ... of the B block this CTA fetches
+      const uint32_t bytes = (diag ? 2u : 3u) * kBlockBytes;      // both B blocks (+ own A block)
+      for (int k = seg.k0; k < seg.k1; ++k) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], bytes);
+        uint8_t* sb = stage_base + stage * kStageBytes;
+        const int row = k * G::BK;
+        tma_load_3d_mcast(&tm_x, &full[stage], sb + rank * kBlockBytes, 0, row, b_group, (uint16_t)0x3);
+        if (!diag) tma_load_3d(&tm_x, &full[stage], sb + 2 * kBlockBytes, 0, row, a_group);
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int s = seg_begin; s < seg_end; ++s) {
+      const PairSeg seg = segs[s];
+      const bool diag = seg.sa == seg.sb;
+      // diagonal super-tile: CTA 1 forms only its diagonal block (B block 1, N = 128)
+      const int n_off = (diag && rank == 1) ? 1 : 0;
+      const int w = 2 - n_off;
+      const uint32_t idesc = make_idesc(FMT, 128 * w);
+      const uint32_t d_tmem = tmem_base + acc * kAccCols;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      for (int k = seg.k0; k < seg.k1; ++k) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sb = smem_u32(stage_base + stage * kStageBytes);
+        const uint32_t sa = diag ? sb + rank * kBlockBytes : sb + 2 * kBlockBytes;
+        const uint32_t sbn = sb + n_off * kBlockBytes;
+#pragma unroll
+        for (int kk = 0; kk < G::NUM_MMA; ++kk) {
+          const uint64_t adesc = make_smem_desc<G::LAYOUT_TYPE>(sa + kk * G::KSTEP_BYTES, G::BOX_BYTES, G::SBO_BYTES);
+          const uint64_t bdesc = make_smem_desc<G::LAYOUT_TYPE>(sbn + kk * G::KSTEP_BYTES, G::BOX_BYTES, G::SBO_BYTES);
+          umma<FMT>(d_tmem, adesc, bdesc, idesc, (k > seg.k0 || kk > 0) ? 1u : 0u);
+        }
+        tc_commit_mcast(&empty[stage], (uint16_t)0x3);  // slot free in BOTH CTAs once these MMAs have read it
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      tc_commit(&tfull[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    const int q = warp - 4;
+    const int epi_tid = threadIdx.x - 128;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t slab_counter = 0;
+    for (int s = seg_begin; s < seg_end; ++s) {
+      const PairSeg seg = segs[s];
+      const bool diag = seg.sa == seg.sb;
+      const int n_off = (diag && rank == 1) ? 1 : 0;
+      const int w = 2 - n_off;
+      const int row0 = (2 * seg.sa + (int)rank) * 128;
+      const int col0 = (2 * seg.sb + n_off) * 128;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int nslab = (row0 < d) ? min(4 * w, (d - col0 + 31) / 32) : 0;
+      for (int sl = 0; sl < nslab; ++sl) {
+        uint8_t* buf = staging + (slab_counter & 1) * kStagingBytes;
+        if (epi_tid == 0) bulk_wait_group_read<1>();
+        named_bar_sync(1, 128);
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols + sl * 32, v);
+        tmem_ld_wait();
+        const uint32_t rbase = smem_u32(buf) + row * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t addr = rbase + ((uint32_t)(c ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * c]), "r"(v[4 * c + 1]),
+                       "r"(v[4 * c + 2]), "r"(v[4 * c + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (epi_tid == 0) {
+          tma_reduce_add_2d(&tm_g, buf, col0 + sl * 32, row0);
+          bulk_commit_group();
+        }
+        ++slab_counter;
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (epi_tid == 0) bulk_wait_group<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's shared memory until here
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+struct DeviceSchedule2 {
+  int nclusters = 0;
+  PairSeg* d_segs = nullptr;
+  int* d_off = nullptr;
+};
+std::mutex g_mu2;
+std::map<std::tuple<int, int64_t, int, int, int>, DeviceSchedule2> g_sched2;
+
+// Panel-major stream-K over super-tiles, one share per cluster (see build_syrk_schedule in syrk_tc.cu).
+void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairSeg>* segs, std::vector<int>* off) {
+  int64_t panel_chunks = syrk_panel_chunks(d);
+  const int nsb = (d + 255) / 256;
+  struct T {
+    int a, b;
+  };
+  std::vector<T> tiles;
+  for (int a = 0; a < nsb; ++a)
+    for (int b = a; b < nsb; ++b) tiles.push_back({a, b});
+  const int64_t ntile = (int64_t)tiles.size();
+  const int64_t total = ntile * kc;
+  const int64_t min_cost = 16;  // chunks of a super-tile per cluster
+  const int ncl = (int)std::max<int64_t>(1, std::min<int64_t>(nclusters_max, total / min_cost));
+  const int64_t npanels = (kc + panel_chunks - 1) / panel_chunks;
+  std::vector<std::vector<PairSeg>> per(ncl);
+  for (int64_t p = 0; p < npanels; ++p) {
+    const int64_t k_lo = p * panel_chunks, k_hi = std::min(kc, k_lo + panel_chunks);
+    const int64_t panel_cost = ntile * (k_hi - k_lo);
+    const int rot = (int)((p * 37) % ncl);
+    int share = 0;
+    int64_t next_cut = panel_cost / ncl, pos = 0;
+    for (const T& t : tiles) {
+      int64_t k = k_lo;
+      while (k < k_hi) {
+        while (share < ncl - 1 && pos >= next_cut) {
+          ++share;
+          next_cut = panel_cost * (share + 1) / ncl;
+        }
+        const int64_t room = (share == ncl - 1) ? (k_hi - k) : (next_cut - pos);
+        const int64_t take = std::min(k_hi - k, std::max<int64_t>(room, 1));
+        per[(share + rot) % ncl].push_back({t.a, t.b, (int)k, (int)(k + take)});
+        k += take;
+        pos += take;
+      }
+    }
+  }
+  segs->clear();
+  off->assign(1, 0);
+  for (int c = 0; c < ncl; ++c) {
+    segs->insert(segs->end(), per[c].begin(), per[c].end());
+    off->push_back((int)segs->size());
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode2 = nullptr;
+
+template <int ELEM_BYTES, int FMT>
+int launch_kernel2(int dev, const DeviceSchedule2& sched, const CUtensorMap& tm_x, const CUtensorMap& tm_g, int d,
+                   cudaStream_t stream) {
+  static std::atomic<bool> attr_done[64];
+  auto kernel = syrk_tc2_kernel<ELEM_BYTES, FMT>;
+  if (dev >= 64 || !attr_done[dev].load(std::memory_order_acquire)) {
+    VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    if (dev < 64) attr_done[dev].store(true, std::memory_order_release);
+  }
+  kernel<<<2 * sched.nclusters, kThreads, kSmemBytes, stream>>>(tm_x, tm_g, sched.d_segs, sched.d_off, d);
+  VLM_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace
+
+// Host view for the CPU tests: segments as {super_row, super_col, k0, k1} per cluster.
+void build_syrk_pair_schedule_host(int64_t kc, int d, int nsm, std::vector<int32_t>* flat, std::vector<int>* off) {
+  std::vector<PairSeg> segs;
+  build_pair_schedule(kc, d, nsm / 2, &segs, off);
+  flat->clear();
+  for (const PairSeg& s : segs) {
+    flat->push_back(s.sa);
+    flat->push_back(s.sb);
+    flat->push_back(s.k0);
+    flat->push_back(s.k1);
+  }
+}
+
+bool syrk_tc2_supported(int dtype, int d, int64_t ldx) {
+  const int elem = (dtype == VLM_F32) ? 4 : 2;
+  return d % (128 / elem) == 0 && ldx >= d;  // whole 128-byte column groups (the 3-D tensor map needs them)
+}
+
+int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,
+                    cudaStream_t stream) {
+  const int elem = (dtype == VLM_F32) ? 4 : 2;
+  const int bk = 128 / elem;
+  const int gc = 128 / elem;
+  VLM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && ((ldx * elem) & 15) == 0, VLM_ERR_ALIGNMENT,
+              "vlm_syrk_accum: x must be 16-byte aligned with a row pitch that is a multiple of 16 bytes");
+  VLM_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0 && (ldg & 3) == 0, VLM_ERR_ALIGNMENT,
+              "vlm_syrk_accum: g must be 16-byte aligned with ldg %% 4 == 0");
+  VLM_REQUIRE(rows < (int64_t)1 << 31, VLM_ERR_INVALID_ARG, "vlm_syrk_accum: rows too large");
+  int dev = 0, nsm = 0;
+  VLM_CUDA(cudaGetDevice(&dev));
+  if (int rc = device_sm_count(&nsm)) return rc;
+  {
+    std::lock_guard<std::mutex> lk(g_mu2);
+    if (!g_encode2) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      VLM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+      VLM_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, VLM_ERR_DRIVER,
+                  "cuTensorMapEncodeTiled not available from the driver");
+      g_encode2 = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+  }
+  const int64_t kc = (rows + bk - 1) / bk;
+  DeviceSchedule2 sched;
+  {
+    std::lock_guard<std::mutex> lk(g_mu2);
+    auto key = std::make_tuple(dev, kc, d, bk, nsm);
+    auto it = g_sched2.find(key);
+    if (it == g_sched2.end()) {
+      std::vector<PairSeg> segs;
+      std::vector<int> off;
+      build_pair_schedule(kc, d, nsm / 2, &segs, &off);
+      DeviceSchedule2 ds;
+      ds.nclusters = (int)off.size() - 1;
+      VLM_CUDA(cudaMalloc(&ds.d_segs, std::max<size_t>(1, segs.size()) * sizeof(PairSeg)));
+      VLM_CUDA(cudaMalloc(&ds.d_off, off.size() * sizeof(int)));
+      VLM_CUDA(cudaMemcpyAsync(ds.d_segs, segs.data(), segs.size() * sizeof(PairSeg), cudaMemcpyHostToDevice, stream));
+      VLM_CUDA(cudaMemcpyAsync(ds.d_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+      VLM_CUDA(cudaStreamSynchronize(stream));
+      it = g_sched2.emplace(key, ds).first;
+    }
+    sched = it->second;
+  }
+
+  CUtensorMap tm_x, tm_g;
+  {
+    const CUtensorMapDataType dt = dtype == VLM_F32    ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                   : dtype == VLM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                       : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    // {column in group, row, column group}: strides row pitch and 128 bytes
+    cuuint64_t gdim[3] = {(cuuint64_t)gc, (cuuint64_t)rows, (cuuint64_t)(d / gc)};
+    cuuint64_t gstr[2] = {(cuuint64_t)ldx * elem, 128};
+    cuuint32_t box[3] = {(cuuint32_t)gc, (cuuint32_t)bk, (cuuint32_t)elem /* groups per 128-column block */};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapSwizzle swz = elem == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+    CUresult r = g_encode2(&tm_x, dt, 3, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VLM_REQUIRE(r == CUDA_SUCCESS, VLM_ERR_DRIVER, "cuTensorMapEncodeTiled(X, 3-D) failed: CUresult %d", (int)r);
+  }
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)d};
+    cuuint64_t gstr[1] = {(cuuint64_t)ldg * 4};
+    cuuint32_t box[2] = {32, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode2(&tm_g, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g, gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VLM_REQUIRE(r == CUDA_SUCCESS, VLM_ERR_DRIVER, "cuTensorMapEncodeTiled(G) failed: CUresult %d", (int)r);
+  }
+  if (dtype == VLM_F32) return launch_kernel2<4, 2>(dev, sched, tm_x, tm_g, d, stream);
+  if (dtype == VLM_BF16) return launch_kernel2<2, 1>(dev, sched, tm_x, tm_g, d, stream);
+  return launch_kernel2<2, 0>(dev, sched, tm_x, tm_g, d, stream);
+}
+
+}  // namespace vlm
