@@ -120,7 +120,7 @@ def run_ours(args):
     torch.backends.cudnn.allow_tf32 = True
     peaks = load_peaks()
 
-    cfg = vlm.vlmo_config(args.model)
+    cfg = vlm.vlmo_config(args.model, attn_impl=args.attn)
     with torch.device(dev):
         model = vlm.VLMo(cfg)
     vlm.init_synthetic_(model.eval(), seed=1)
@@ -150,7 +150,7 @@ def run_ours(args):
     dev_batches = [{"image": [hb["image"][0].to(dev)], **{k: hb[k].to(dev) for k in ("text_ids", "text_masks", "text_labels")}}
                    for hb in host_batches]
 
-    def step(batch):
+    def step(batch, amp=amp):
         with torch.no_grad():
             if amp is None:
                 return model(batch)
@@ -229,7 +229,8 @@ def run_ours(args):
     peak_tf = peaks["bf16_tflops_sustained"] * (1.0 if sixteen else 0.5)
     achieved_tf = tot_flops / (tot_ms * 1e-3) * 1e-12 if tot_ms > 0 else 0.0
     roofline = {
-        "kernel": "syrk_tc_kernel (tcgen05 kind::tf32, TMA, TMEM)" if not sixteen else "syrk_tc_kernel (mixed tf32 / f16 kinds under autocast)",
+        "kernel": "syrk_tc2_kernel (CTA pairs, TMA multicast, tcgen05 kind::tf32, TMEM accumulators, TMA reduce-add)" if not sixteen
+        else "syrk_tc2_kernel (mixed kind::tf32 / kind::f16 launches under autocast)",
         "bound": "tensor", "achieved": round(achieved_tf, 2), "peak": round(peak_tf, 1), "unit": "TFLOP/s",
         "frac": round(achieved_tf / peak_tf, 4), "traffic": None,
         "peak_source": f"{peaks['source']}: bf16_tflops_sustained{' / 2 (TF32)' if not sixteen else ''}",
@@ -265,6 +266,23 @@ def run_ours(args):
         parity = {n: float(((cache.gram(n).double() - probe[n]).norm() / probe[n].norm()).item()) for n in names}
         cache.reset()
 
+    # ---- informational: the same calibration with faster stock-torch forwards ----------------------
+    variants = {}
+    if not args.no_variants:
+        attn_mods = [m for m in model.modules() if hasattr(m, "attn_impl")]
+        for vname, impl, vamp in (("fp32_tf32_sdpa", "sdpa", None), ("autocast_bf16_sdpa", "sdpa", torch.bfloat16)):
+            for m in attn_mods:
+                m.attn_impl = impl
+            for i in range(3):
+                step(dev_batches[i % 2], vamp)
+            cache.reset()
+            vms, _, _, _ = timed(lambda i: step(dev_batches[i % 2], vamp), args.steps, with_allreduce=True)
+            variants[vname] = {"value": round(world * B * args.steps / (vms * 1e-3), 2), "unit": "samples/s",
+                               "ms_per_step": round(vms / args.steps, 3)}
+        for m in attn_mods:
+            m.attn_impl = args.attn
+        cache.reset()
+
     # ---- kernel (b): interpolation merge of this checkpoint ---------------------------------------
     merge = bench_merge(vlm, model, cfg, dev, group, world, rank, peaks, args)
 
@@ -277,11 +295,11 @@ def run_ours(args):
             "data": "synthetic (hash-seeded images U(-1,1) 384px + 40-token ids; random-init VLMo weights)",
             "config": {"workload": f"RegMean Gram caching, VLMo-{args.model} all_moe, {B} x (577 image + 40 text tokens) per GPU per step; "
                                    "96 Grams (72 x 768^2 + 24 x 3072^2)" if args.model == "base" else f"RegMean Gram caching, VLMo-{args.model} all_moe",
-                       "global_batch": world * B, "parallelism": f"dp{world}", "forward": "stock torch, " + ("fp32 with TF32 matmuls" if not sixteen else f"autocast {args.autocast}"),
+                       "global_batch": world * B, "parallelism": f"dp{world}", "forward": f"stock torch ({args.attn} attention), " + ("fp32 with TF32 matmuls" if not sixteen else f"autocast {args.autocast}"),
                        "l2": "inputs larger than L2 (each step streams >2 GB of weights and activations)",
                        "allreduce_ms_in_timed_region": round(ar_ms, 3)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "merge": merge, "gram_parity_rel_fro": parity,
+            "roofline": roofline, "merge": merge, "gram_parity_rel_fro": parity, "forward_variants": variants,
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_sample(args.model, budget_s=25.0)
@@ -466,6 +484,9 @@ def main():
     ap.add_argument("--model", default="base", choices=["base", "large", "tiny"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--autocast", default="fp32", choices=["fp32", "bf16", "fp16"])
+    ap.add_argument("--attn", default="reference", choices=["reference", "sdpa"],
+                    help="attention of the stock-torch forward: the reference's explicit softmax, or torch SDPA")
+    ap.add_argument("--no-variants", action="store_true", help="skip the extra (informational) forward variants")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true",
                     help="for ncu launch lists: run exactly --warmup + --steps calibration steps and exit (no JSON line)")

@@ -1,0 +1,86 @@
+"""Multi-GPU paths on real devices (NCCL, 2 ranks): data-parallel Gram caching with the single all-reduce,
+and tensor-sharded merges with the final all-gather.  Skipped on boxes with fewer than 2 GPUs; the same
+host logic is covered on CPU with gloo in tests/test_dist_cpu.py."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    import torch.distributed as dist
+
+    import vl_merging_b200 as vlm
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        cfg = vlm.vlmo_config("tiny")
+        model = vlm.init_synthetic_(vlm.VLMo(cfg).eval(), seed=1).cuda()
+        cache = vlm.GramCache()
+        cache.register(model)
+        with torch.no_grad():
+            model(vlm.synthetic_batch(2, cfg, seed=50 + rank, device="cuda"))   # this rank's shard of the calibration set
+        cache.all_reduce()
+        grams = cache.state_dict()
+        sd = {k: v.detach() for k, v in model.state_dict().items()}
+        mcfg = dict(vlffn_start_layer_index=10, only_activate_used_experts=False, merge_ratio=0.5, sum_lambda=0.75,
+                    scaling_for_non_diag=0.9, loss_names={"irtr": 1.0, "vqa": 0, "nlvr2": 0})
+        merged = vlm.merge_weights(sd, mcfg, group=dist.group.WORLD)
+        rm = vlm.regmean(sd, mcfg, gram_matrices=grams, group=dist.group.WORLD)
+        pick = ["transformer.blocks.0.attn.qkv.weight", "transformer.blocks.11.mlp.fc2.weight", "transformer.blocks.4.norm2.bias"]
+        ret[rank] = {
+            "grams": {k: grams[k].numpy() for k in ("transformer.blocks.0.attn.v", "transformer.blocks.7.mlp.l.fc2")},
+            "n_grams": len(grams),
+            "merged": {k: merged[k].cpu().numpy() for k in pick},
+            "regmean": {k: rm[k].cpu().numpy() for k in pick},
+        }
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_calibration_and_sharded_merge():
+    import torch.multiprocessing as mp
+
+    import vl_merging_b200 as vlm
+
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    r0, r1 = ret[0], ret[1]
+    assert r0["n_grams"] == r1["n_grams"] == 96
+    # single-process oracle for the reduced result: one cache over both shards
+    cfg = vlm.vlmo_config("tiny")
+    model = vlm.init_synthetic_(vlm.VLMo(cfg).eval(), seed=1).cuda()
+    cache = vlm.GramCache()
+    cache.register(model)
+    with torch.no_grad():
+        for rank in range(2):
+            model(vlm.synthetic_batch(2, cfg, seed=50 + rank, device="cuda"))
+    want = cache.state_dict()
+    for k, g in r0["grams"].items():
+        assert np.array_equal(g, r1["grams"][k])
+        assert np.linalg.norm(g - want[k].numpy()) <= 1e-5 * np.linalg.norm(want[k].numpy())
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    mcfg = dict(vlffn_start_layer_index=10, only_activate_used_experts=False, merge_ratio=0.5, sum_lambda=0.75,
+                scaling_for_non_diag=0.9, loss_names={"irtr": 1.0, "vqa": 0, "nlvr2": 0})
+    single = vlm.merge_weights(sd, mcfg)
+    single_rm = vlm.regmean(sd, mcfg, gram_matrices=want)
+    for k in r0["merged"]:
+        assert np.array_equal(r0["merged"][k], r1["merged"][k])
+        assert np.array_equal(r0["merged"][k], single[k].cpu().numpy())          # sharding does not change a bit
+        a, b = r0["regmean"][k], single_rm[k].cpu().numpy()
+        assert np.array_equal(r0["regmean"][k], r1["regmean"][k])
+        assert np.linalg.norm(a - b) <= 1e-6 * np.linalg.norm(b)

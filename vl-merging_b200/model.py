@@ -40,10 +40,11 @@ class Attention(nn.Module):
     position bias, fp32 logits.  The qkv projection is applied with F.linear, not self.qkv(x) — as in
     the reference (vision_transformer.py:337), which is why the qkv Gram is hooked on THIS module."""
 
-    def __init__(self, dim, num_heads):
+    def __init__(self, dim, num_heads, attn_impl="reference"):
         super().__init__()
         self.num_heads = num_heads
         self.scale = (dim // num_heads) ** -0.5
+        self.attn_impl = attn_impl  # "reference": the reference's explicit fp32 softmax; "sdpa": torch's fused kernel
         self.qkv = nn.Linear(dim, dim * 3, bias=False)
         self.q_bias = nn.Parameter(torch.zeros(dim))
         self.v_bias = nn.Parameter(torch.zeros(dim))
@@ -53,6 +54,16 @@ class Attention(nn.Module):
         b, n, c = x.shape
         bias = torch.cat((self.q_bias, torch.zeros_like(self.v_bias), self.v_bias))
         qkv = F.linear(x, self.qkv.weight, bias).reshape(b, n, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4)
+        if self.attn_impl == "sdpa":
+            # same math through F.scaled_dot_product_attention (still stock torch): the relative position
+            # bias and the key-padding mask become one additive mask
+            add = relative_position_bias.unsqueeze(0).to(qkv.dtype) if relative_position_bias is not None else None
+            if mask is not None and not bool(mask.all()):
+                pad = torch.zeros(b, 1, 1, n, dtype=qkv.dtype, device=x.device).masked_fill(
+                    ~mask.bool()[:, None, None, :], float("-inf"))
+                add = pad if add is None else add + pad
+            x = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], attn_mask=add, scale=self.scale)
+            return self.proj(x.transpose(1, 2).reshape(b, n, c))
         q, k, v = qkv[0] * self.scale, qkv[1], qkv[2]
         attn = q.float() @ k.float().transpose(-2, -1)
         if relative_position_bias is not None:
@@ -68,16 +79,16 @@ class Block(nn.Module):
     """One multiway block.  experts = ("v","l") / ("v","l","vl") gives the modality-specific (all_moe)
     layout with per-expert attention, MLP and both LayerNorms; experts = None the shared (ufo) one."""
 
-    def __init__(self, dim, num_heads, mlp_ratio, experts):
+    def __init__(self, dim, num_heads, mlp_ratio, experts, attn_impl="reference"):
         super().__init__()
         self.experts = experts
         hidden = int(dim * mlp_ratio)
         ln = lambda: nn.LayerNorm(dim, eps=1e-6)  # noqa: E731
         if experts is None:
-            self.attn, self.norm1 = Attention(dim, num_heads), ln()
+            self.attn, self.norm1 = Attention(dim, num_heads, attn_impl), ln()
             self.mlp, self.norm2 = Mlp(dim, hidden), ln()
         else:
-            self.attn = nn.ModuleDict({m: Attention(dim, num_heads) for m in experts})
+            self.attn = nn.ModuleDict({m: Attention(dim, num_heads, attn_impl) for m in experts})
             self.norm1 = nn.ModuleDict({m: ln() for m in experts})
             self.mlp = nn.ModuleDict({m: Mlp(dim, hidden) for m in experts})
             self.norm2 = nn.ModuleDict({m: ln() for m in experts})
@@ -112,7 +123,8 @@ class Transformer(nn.Module):
         self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
         self.mask_token = nn.Parameter(torch.zeros(1, 1, dim))
         self.blocks = nn.ModuleList(
-            [Block(dim, cfg["num_heads"], cfg["mlp_ratio"], experts_for_layer(i)) for i in range(cfg["num_layers"])])
+            [Block(dim, cfg["num_heads"], cfg["mlp_ratio"], experts_for_layer(i), cfg.get("attn_impl", "reference"))
+             for i in range(cfg["num_layers"])])
         self.norm = nn.LayerNorm(dim, eps=1e-6)
 
     def visual_embed(self, img):
@@ -147,7 +159,7 @@ class _Head(nn.Module):
 DEFAULT_CONFIG = dict(
     hidden_size=768, num_heads=12, num_layers=12, mlp_ratio=4, image_size=384, patch_size=16,
     max_text_len=40, max_text_len_of_initckpt=196, vocab_size=30522, vlffn_start_layer_index=10,
-    use_moe=True,
+    use_moe=True, attn_impl="reference",
 )
 
 
