@@ -286,6 +286,17 @@ def run_ours(args):
     # ---- kernel (b): interpolation merge of this checkpoint ---------------------------------------
     merge = bench_merge(vlm, model, cfg, dev, group, world, rank, peaks, args)
 
+    # ---- config 3: full RegMean merge from the cached Grams (kernel (c) + cuSOLVER, timed separately) ----
+    regmean = None
+    if not args.no_regmean:
+        cache.reset()
+        for i in range(2):  # 2 x 64 x 40 = 5120 text rows >= 3072: every summed Gram is full rank
+            step(dev_batches[i % 2])
+        if world > 1:
+            cache.all_reduce(group)
+        regmean = bench_regmean(vlm, model, cfg, cache, dev, group, world, args)
+        cache.reset()
+
     out = None
     if rank == 0:
         out = {
@@ -299,7 +310,8 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (each step streams >2 GB of weights and activations)",
                        "allreduce_ms_in_timed_region": round(ar_ms, 3)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "merge": merge, "gram_parity_rel_fro": parity, "forward_variants": variants,
+            "roofline": roofline, "merge": merge, "regmean": regmean, "gram_parity_rel_fro": parity,
+            "forward_variants": variants,
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_sample(args.model, budget_s=25.0)
@@ -385,6 +397,45 @@ def bench_merge(vlm, model, cfg, dev, group, world, rank, peaks, args):
         "e2e": {"value": round(nbytes / dt * 1e-9, 2), "unit": "GB/s", "seconds": round(dt, 4),
                 "h2d_bytes": stats.get("h2d_bytes"), "d2h_bytes": stats.get("d2h_bytes"), "bit_exact_vs_torch": bool(ok)},
     }
+
+
+def bench_regmean(vlm, model, cfg, cache, dev, group, world, args):
+    """RegMean of the bench checkpoint with the Grams just cached on the device (scaling_for_non_diag = 0.9):
+    wall time of the whole merge, split into the W*Ghat GEMMs (kernel (c), fp64 DMMA) and the SPD solves
+    (cuSOLVER), plus one linear checked against torch fp64 on the same Grams."""
+    import torch.distributed as dist
+
+    mcfg = dict(vlffn_start_layer_index=cfg["vlffn_start_layer_index"], scaling_for_non_diag=0.9,
+                loss_names={"irtr": 1, "vqa": 0, "nlvr2": 0})
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    L = cfg["num_layers"]
+    vlm.regmean(sd, mcfg, device=dev, num_layers=L, group=group, gram_matrices=cache)  # warm-up (cuSOLVER handle, plans)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    stats = {}
+    t0 = time.perf_counter()
+    merged = vlm.regmean(sd, mcfg, device=dev, num_layers=L, group=group, gram_matrices=cache, stats=stats)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    # check: layer 0 attention projection, torch fp64 on the same device Grams
+    a = 0.9
+    num = den = 0
+    for m in ("v", "l"):
+        g = cache.gram(f"transformer.blocks.0.attn.{m}.proj").double()
+        gh = a * g + (1 - a) * torch.diag(torch.diag(g))
+        num = num + sd[f"transformer.blocks.0.attn.{m}.proj.weight"].double() @ gh
+        den = den + gh
+    want = torch.linalg.solve(den, num.T).T
+    got = merged["transformer.blocks.0.attn.proj.weight"]
+    err = ((got - want).norm() / want.norm()).item()
+    d, h = cfg["hidden_size"], cfg["hidden_size"] * cfg["mlp_ratio"]
+    rhs_flops = L * 2 * 2 * (3 * d * d * d + d * d * d + h * d * d + d * h * h)
+    return {"seconds": round(dt, 4), "rhs_seconds": round(stats.get("rhs_seconds", 0.0), 4),
+            "solve_seconds": round(stats.get("solve_seconds", 0.0), 4),
+            "rhs_fp64_tflops": round(rhs_flops / max(stats.get("rhs_seconds", 1e-9), 1e-9) * 1e-12 / world, 2),
+            "linear_problems": 4 * L, "dtype": "f64", "check_rel_err_vs_torch_fp64": err,
+            "note": "RHS = fp64 DMMA kernel incl. scale_G and sum of Grams; solve = cuSOLVER potrf/potrs (off the hot path)"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -487,6 +538,7 @@ def main():
     ap.add_argument("--attn", default="reference", choices=["reference", "sdpa"],
                     help="attention of the stock-torch forward: the reference's explicit softmax, or torch SDPA")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra (informational) forward variants")
+    ap.add_argument("--no-regmean", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true",
                     help="for ncu launch lists: run exactly --warmup + --steps calibration steps and exit (no JSON line)")

@@ -22,6 +22,7 @@
 // walk the same segment list, so they stay in lock-step by construction.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -69,6 +70,13 @@ __device__ __forceinline__ void tma_load_3d_mcast(const CUtensorMap* tm, uint64_
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// L2 prefetch of one box (no shared memory involved): the later real load then hits L2
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 // tcgen05.commit arriving on the mbarrier at this smem offset in every CTA of `mask`
 __device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -85,7 +93,7 @@ struct PairSeg {
 template <int ELEM_BYTES, int FMT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
-                const PairSeg* __restrict__ segs, const int* __restrict__ seg_off, int d) {
+                const PairSeg* __restrict__ segs, const int* __restrict__ seg_off, int d, int prefetch_dist) {
   using G = Geo<ELEM_BYTES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -133,6 +141,22 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     // ===== TMA producer =====
     int stage = 0;
     uint32_t phase = 0;
+    // look-ahead cursor: prefetches into L2 the boxes this CTA will load `prefetch_dist` chunks from now
+    // (its own A block and the B block it multicasts), so that the real loads see L2-hit latency even on
+    // the first touch of a row panel
+    int ps = seg_begin, pk = (seg_begin < seg_end) ? segs[seg_begin].k0 : 0;
+    auto prefetch_next = [&]() {
+      if (ps >= seg_end) return;
+      const PairSeg p = segs[ps];
+      const int row = pk * G::BK;
+      tma_prefetch_l2_3d(&tm_x, 0, row, (2 * p.sb + (int)rank) * G::GB);
+      if (p.sa != p.sb) tma_prefetch_l2_3d(&tm_x, 0, row, (2 * p.sa + (int)rank) * G::GB);
+      if (++pk >= p.k1) {
+        ++ps;
+        if (ps < seg_end) pk = segs[ps].k0;
+      }
+    };
+    for (int i = 0; i < prefetch_dist; ++i) prefetch_next();
     for (int s = seg_begin; s < seg_end; ++s) {
       const PairSeg seg = segs[s];
       const bool diag = seg.sa == seg.sb;
@@ -140,6 +164,7 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       const int b_group = (2 * seg.sb + (int)rank) * G::GB;       // ... of the B block this CTA fetches
       const uint32_t bytes = (diag ? 2u : 3u) * kBlockBytes;      // both B blocks (+ own A block)
       for (int k = seg.k0; k < seg.k1; ++k) {
+        if (prefetch_dist > 0) prefetch_next();
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full[stage], bytes);
         uint8_t* sb = stage_base + stage * kStageBytes;
@@ -252,8 +277,79 @@ struct DeviceSchedule2 {
 std::mutex g_mu2;
 std::map<std::tuple<int, int64_t, int, int, int>, DeviceSchedule2> g_sched2;
 
-// Panel-major stream-K over super-tiles, one share per cluster (see build_syrk_schedule in syrk_tc.cu).
+// Work decomposition for the CTA-pair kernel: K-ALIGNED tile ownership.
+//
+// Every cluster sweeps the rows of X from the top for "its" super-tile, so at any moment all clusters read
+// the same thin band of rows: X streams from HBM once, every re-read (each column block is used by ~nsb
+// tiles) hits L2, and no row panel has to fit in L2.  T super-tiles over C clusters:
+//   * T >= C: floor(T/C) rounds of whole tiles (cluster c owns tiles c, c+C, ...), then the T mod C
+//     left-over tiles are cut along K into C equal shares (stream-K) so that nobody idles;
+//   * T <  C: every tile is cut along K into m = floor(C/T) equal pieces with the SAME boundaries for all
+//     tiles (clusters on different tiles then stay aligned in K); T*m clusters are used.
+// A K range longer than seg_cap chunks is processed as consecutive segments of at most seg_cap chunks:
+// each ends with its own reduce-add into G (hidden behind the next segment's mainloop by the double-
+// buffered TMEM accumulator), which bounds the tensor core's truncating fp32 accumulation.
+// VLM_SYRK_SCHEDULE=panel selects the previous panel-major stream-K (kept for A/B measurements).
+void build_pair_schedule_panel(int64_t kc, int d, int nclusters_max, std::vector<PairSeg>* segs, std::vector<int>* off);
+
 void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairSeg>* segs, std::vector<int>* off) {
+  if (const char* e = getenv("VLM_SYRK_SCHEDULE"))
+    if (!strcmp(e, "panel")) return build_pair_schedule_panel(kc, d, nclusters_max, segs, off);
+  int64_t seg_cap = 256;  // chunks per accumulation (8192 fp32 rows / 16384 16-bit rows)
+  if (const char* e = getenv("VLM_SYRK_SEG_CHUNKS")) seg_cap = std::max(1, atoi(e));
+  const int nsb = (d + 255) / 256;
+  struct T {
+    int a, b;
+  };
+  std::vector<T> tiles;
+  for (int a = 0; a < nsb; ++a)
+    for (int b = a; b < nsb; ++b) tiles.push_back({a, b});
+  const int64_t ntile = (int64_t)tiles.size();
+  const int64_t min_chunks = 16;  // do not cut a K range below this: the 128 KB epilogue must stay small
+  const int C = nclusters_max;
+  std::vector<std::vector<PairSeg>> per;
+  auto emit = [&](int c, const T& t, int64_t k0, int64_t k1) {
+    if (k1 <= k0) return;
+    const int64_t pieces = (k1 - k0 + seg_cap - 1) / seg_cap;
+    for (int64_t i = 0; i < pieces; ++i) {
+      const int64_t a = k0 + (k1 - k0) * i / pieces, b = k0 + (k1 - k0) * (i + 1) / pieces;
+      per[c].push_back({t.a, t.b, (int)a, (int)b});
+    }
+  };
+  per.resize(C);
+  const int64_t rounds = ntile / C;  // whole tiles per cluster, all clusters sweeping K from 0 together
+  for (int64_t r = 0; r < rounds; ++r)
+    for (int c = 0; c < C; ++c) emit(c, tiles[r * C + c], 0, kc);
+  // The R = T mod C left-over tiles (all T tiles when T < C) are cut along K into P equal pieces with the
+  // same boundaries for every tile; the (piece, tile) items are dealt round-robin in piece-major order,
+  // so concurrently processed items belong to the same one or two pieces (K-aligned).  P minimises the
+  // makespan ceil(R*P/C)/P among piece lengths between min_chunks.. and seg_cap chunks.
+  const int64_t rem = ntile - rounds * C;
+  if (rem > 0) {
+    const int64_t p_lo = std::max<int64_t>(1, (kc + seg_cap - 1) / seg_cap);
+    const int64_t p_hi = std::max<int64_t>(p_lo, kc / (kc >= 8 * 64 ? 64 : min_chunks));
+    int64_t best_p = p_lo;
+    double best = 1e30;
+    for (int64_t p = p_lo; p <= p_hi; ++p) {
+      const double makespan = (double)((rem * p + C - 1) / C) / (double)p;
+      if (makespan < best - 1e-9) best = makespan, best_p = p;
+    }
+    int64_t q = 0;
+    for (int64_t p = 0; p < best_p; ++p)
+      for (int64_t t = 0; t < rem; ++t, ++q)
+        emit((int)(q % C), tiles[rounds * C + t], kc * p / best_p, kc * (p + 1) / best_p);
+  }
+  while (!per.empty() && per.back().empty()) per.pop_back();  // clusters without work are not launched
+  segs->clear();
+  off->assign(1, 0);
+  for (auto& v : per) {
+    segs->insert(segs->end(), v.begin(), v.end());
+    off->push_back((int)segs->size());
+  }
+}
+
+// Panel-major stream-K over super-tiles, one share per cluster (see build_syrk_schedule in syrk_tc.cu).
+void build_pair_schedule_panel(int64_t kc, int d, int nclusters_max, std::vector<PairSeg>* segs, std::vector<int>* off) {
   int64_t panel_chunks = syrk_panel_chunks(d);
   const int nsb = (d + 255) / 256;
   struct T {
@@ -311,7 +407,11 @@ int launch_kernel2(int dev, const DeviceSchedule2& sched, const CUtensorMap& tm_
     VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     if (dev < 64) attr_done[dev].store(true, std::memory_order_release);
   }
-  kernel<<<2 * sched.nclusters, kThreads, kSmemBytes, stream>>>(tm_x, tm_g, sched.d_segs, sched.d_off, d);
+  static const int prefetch_dist = [] {
+    const char* e = getenv("VLM_SYRK_PREFETCH");
+    return e ? std::max(0, atoi(e)) : 0;
+  }();
+  kernel<<<2 * sched.nclusters, kThreads, kSmemBytes, stream>>>(tm_x, tm_g, sched.d_segs, sched.d_off, d, prefetch_dist);
   VLM_CUDA(cudaGetLastError());
   count_launch();
   return 0;
