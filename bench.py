@@ -224,6 +224,17 @@ def run_ours(args):
         s[1] += dms
         s[2] += syrk_flops(rows, d)
     n_ev = max(len(cache.events), 1)
+    # DRAM traffic per launch of the dominant shape (36928 x 3072 fp32) from the committed ncu --set full capture
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "r01_syrk_tc2_f32_36928x3072.summary.csv")
+    if os.path.exists(prof):
+        vals = {}
+        for line in open(prof):
+            parts = line.strip().split(",")
+            if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                vals[parts[0]] = float(parts[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(parts[1], 1.0)
+        if len(vals) == 2:
+            traffic = int(sum(vals.values()))
     sixteen = amp is not None
     # TF32 runs at half the bf16 tensor rate; the MEASURED bf16 figure (sustained: kernel timed inside a long step)
     peak_tf = peaks["bf16_tflops_sustained"] * (1.0 if sixteen else 0.5)
@@ -232,7 +243,9 @@ def run_ours(args):
         "kernel": "syrk_tc2_kernel (CTA pairs, TMA multicast, tcgen05 kind::tf32, TMEM accumulators, TMA reduce-add)" if not sixteen
         else "syrk_tc2_kernel (mixed kind::tf32 / kind::f16 launches under autocast)",
         "bound": "tensor", "achieved": round(achieved_tf, 2), "peak": round(peak_tf, 1), "unit": "TFLOP/s",
-        "frac": round(achieved_tf / peak_tf, 4), "traffic": None,
+        "frac": round(achieved_tf / peak_tf, 4), "traffic": traffic,
+        "traffic_note": "dram read+write bytes of ONE 36928x3072 fp32 launch (ncu --set full, profiles/); its algorithmic minimum is one read of X = 453.8 MB",
+        "frac_of_nominal_1.1PF_tf32": round(achieved_tf / 1100.0, 4) if not sixteen else None,
         "peak_source": f"{peaks['source']}: bf16_tflops_sustained{' / 2 (TF32)' if not sixteen else ''}",
         "flops_per_launch_avg": tot_flops / n_ev, "ms_per_launch_avg": tot_ms / n_ev, "launches_timed": len(cache.events),
         "syrk_share_of_step": round(tot_ms / (ms if ms > 0 else 1), 4),
