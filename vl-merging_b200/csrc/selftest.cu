@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <vector>
 
 #include "../../include/vlmerge.h"
@@ -375,6 +376,26 @@ static void regmean_case(int out_f, int in_f, double alpha) {
 
 int main(int argc, char** argv) {
   const bool full = argc > 1 && !strcmp(argv[1], "full");
+  if (argc >= 2 && !strcmp(argv[1], "overhead")) {  // host cost of one vlm_syrk_accum call (tiny problem, async)
+    float *dx, *dg;
+    CK(cudaMalloc(&dx, 64 * 128 * 4));
+    CK(cudaMalloc(&dg, 128 * 128 * 4));
+    CK(cudaMemset(dx, 0, 64 * 128 * 4));
+    CK(cudaMemset(dg, 0, 128 * 128 * 4));
+    for (int i = 0; i < 10; ++i) VK(vlm_syrk_accum(dx, VLM_F32, 64, 128, 128, dg, 128, nullptr));
+    CK(cudaDeviceSynchronize());
+    const int n = 2000;
+    timespec t0, t1, t2;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int i = 0; i < n; ++i) VK(vlm_syrk_accum(dx, VLM_F32, 64, 128, 128, dg, 128, nullptr));
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    CK(cudaDeviceSynchronize());
+    clock_gettime(CLOCK_MONOTONIC, &t2);
+    auto us = [](timespec a, timespec b) { return (b.tv_sec - a.tv_sec) * 1e6 + (b.tv_nsec - a.tv_nsec) * 1e-3; };
+    printf("OVERHEAD vlm_syrk_accum: %.2f us/call to enqueue (host), %.2f us/call until drained (GPU-bound)\n",
+           us(t0, t1) / n, us(t0, t2) / n);
+    return 0;
+  }
   if (argc >= 6 && !strcmp(argv[1], "case")) {  // selftest case <f32|bf16|f16> <rows> <d> <iters> [positive]
     const int64_t rows = atoll(argv[3]);
     const int d = atoi(argv[4]), iters = atoi(argv[5]), mode = argc > 6 ? atoi(argv[6]) : 0;

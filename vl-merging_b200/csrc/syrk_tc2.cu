@@ -90,21 +90,29 @@ struct PairSeg {
   int32_t sa, sb, k0, k1;
 };
 
-template <int ELEM_BYTES, int FMT>
+// HALF = 1 halves the rows per pipeline stage (16 fp32 / 32 16-bit rows) and doubles the stage count: same
+// bytes in flight, finer grain (7/8 instead of 3/4 of the buffer can be ahead of the tensor core).
+template <int ELEM_BYTES, int FMT, int HALF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
                 const PairSeg* __restrict__ segs, const int* __restrict__ seg_off, int d, int prefetch_dist) {
   using G = Geo<ELEM_BYTES>;
+  constexpr int kRows = G::BK >> HALF;            // rows of X per pipeline stage
+  constexpr int kBlk = kBlockBytes >> HALF;       // bytes of one 128-column block per stage
+  constexpr int kBox = G::BOX_BYTES >> HALF;      // bytes of one column group per stage (= LBO)
+  constexpr int kNumMma = G::NUM_MMA >> HALF;
+  constexpr int kNStages = kStages << HALF;
+  constexpr int kStageB = 3 * kBlk;               // [B0][B1][A]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  uint8_t* staging = smem + kStages * kStageBytes;
+  uint8_t* staging = smem + kNStages * kStageB;
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
   uint64_t* full = bars;
-  uint64_t* empty = bars + kStages;
-  uint64_t* tfull = bars + 2 * kStages;
-  uint64_t* tempty = bars + 2 * kStages + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* empty = bars + kNStages;
+  uint64_t* tfull = bars + 2 * kNStages;
+  uint64_t* tempty = bars + 2 * kNStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNStages + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -118,7 +126,7 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     tma_prefetch_desc(&tm_g);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kNStages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 2);  // this CTA's MMA commit + the peer's
     }
@@ -148,7 +156,7 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     auto prefetch_next = [&]() {
       if (ps >= seg_end) return;
       const PairSeg p = segs[ps];
-      const int row = pk * G::BK;
+      const int row = pk * kRows;
       tma_prefetch_l2_3d(&tm_x, 0, row, (2 * p.sb + (int)rank) * G::GB);
       if (p.sa != p.sb) tma_prefetch_l2_3d(&tm_x, 0, row, (2 * p.sa + (int)rank) * G::GB);
       if (++pk >= p.k1) {
@@ -162,16 +170,16 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       const bool diag = seg.sa == seg.sb;
       const int a_group = (2 * seg.sa + (int)rank) * G::GB;       // first column group of this CTA's A block
       const int b_group = (2 * seg.sb + (int)rank) * G::GB;       // ... of the B block this CTA fetches
-      const uint32_t bytes = (diag ? 2u : 3u) * kBlockBytes;      // both B blocks (+ own A block)
+      const uint32_t bytes = (diag ? 2u : 3u) * kBlk;             // both B blocks (+ own A block)
       for (int k = seg.k0; k < seg.k1; ++k) {
         if (prefetch_dist > 0) prefetch_next();
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full[stage], bytes);
-        uint8_t* sb = stage_base + stage * kStageBytes;
-        const int row = k * G::BK;
-        tma_load_3d_mcast(&tm_x, &full[stage], sb + rank * kBlockBytes, 0, row, b_group, (uint16_t)0x3);
-        if (!diag) tma_load_3d(&tm_x, &full[stage], sb + 2 * kBlockBytes, 0, row, a_group);
-        if (++stage == kStages) {
+        uint8_t* sb = stage_base + stage * kStageB;
+        const int row = k * kRows;
+        tma_load_3d_mcast(&tm_x, &full[stage], sb + rank * kBlk, 0, row, b_group, (uint16_t)0x3);
+        if (!diag) tma_load_3d(&tm_x, &full[stage], sb + 2 * kBlk, 0, row, a_group);
+        if (++stage == kNStages) {
           stage = 0;
           phase ^= 1;
         }
@@ -196,17 +204,17 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       for (int k = seg.k0; k < seg.k1; ++k) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t sb = smem_u32(stage_base + stage * kStageBytes);
-        const uint32_t sa = diag ? sb + rank * kBlockBytes : sb + 2 * kBlockBytes;
-        const uint32_t sbn = sb + n_off * kBlockBytes;
+        const uint32_t sb = smem_u32(stage_base + stage * kStageB);
+        const uint32_t sa = diag ? sb + rank * kBlk : sb + 2 * kBlk;
+        const uint32_t sbn = sb + n_off * kBlk;
 #pragma unroll
-        for (int kk = 0; kk < G::NUM_MMA; ++kk) {
-          const uint64_t adesc = make_smem_desc<G::LAYOUT_TYPE>(sa + kk * G::KSTEP_BYTES, G::BOX_BYTES, G::SBO_BYTES);
-          const uint64_t bdesc = make_smem_desc<G::LAYOUT_TYPE>(sbn + kk * G::KSTEP_BYTES, G::BOX_BYTES, G::SBO_BYTES);
+        for (int kk = 0; kk < kNumMma; ++kk) {
+          const uint64_t adesc = make_smem_desc<G::LAYOUT_TYPE>(sa + kk * G::KSTEP_BYTES, kBox, G::SBO_BYTES);
+          const uint64_t bdesc = make_smem_desc<G::LAYOUT_TYPE>(sbn + kk * G::KSTEP_BYTES, kBox, G::SBO_BYTES);
           umma<FMT>(d_tmem, adesc, bdesc, idesc, (k > seg.k0 || kk > 0) ? 1u : 0u);
         }
         tc_commit_mcast(&empty[stage], (uint16_t)0x3);  // slot free in BOTH CTAs once these MMAs have read it
-        if (++stage == kStages) {
+        if (++stage == kNStages) {
           stage = 0;
           phase ^= 1;
         }
@@ -292,7 +300,9 @@ std::map<std::tuple<int, int64_t, int, int, int>, DeviceSchedule2> g_sched2;
 // VLM_SYRK_SCHEDULE=panel selects the previous panel-major stream-K (kept for A/B measurements).
 void build_pair_schedule_panel(int64_t kc, int d, int nclusters_max, std::vector<PairSeg>* segs, std::vector<int>* off);
 
-void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairSeg>* segs, std::vector<int>* off) {
+// chunk_scale = schedule chunks per 128-byte-deep chunk (2 when the kernel runs half-height stages)
+void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairSeg>* segs, std::vector<int>* off,
+                         int chunk_scale = 1) {
   if (const char* e = getenv("VLM_SYRK_SCHEDULE"))
     if (!strcmp(e, "panel")) return build_pair_schedule_panel(kc, d, nclusters_max, segs, off);
   // chunks per accumulation: 4096 fp32 rows / 8192 16-bit rows.  Measured on the B200 with all-positive
@@ -300,6 +310,7 @@ void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairS
   // 2.2e-5 / 5.0e-5 / 8.8e-5 (bf16), at 742 / 753 / 766 / 779 TFLOP/s.
   int64_t seg_cap = 128;
   if (const char* e = getenv("VLM_SYRK_SEG_CHUNKS")) seg_cap = std::max(1, atoi(e));
+  seg_cap *= chunk_scale;
   const int nsb = (d + 255) / 256;
   struct T {
     int a, b;
@@ -308,7 +319,7 @@ void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairS
   for (int a = 0; a < nsb; ++a)
     for (int b = a; b < nsb; ++b) tiles.push_back({a, b});
   const int64_t ntile = (int64_t)tiles.size();
-  const int64_t min_chunks = 8;  // do not cut a K range below this: every piece pays a 128 KB epilogue per CTA
+  const int64_t min_chunks = 8 * chunk_scale;  // do not cut a K range below this: every piece pays a 128 KB epilogue per CTA
   const int C = nclusters_max;
   std::vector<std::vector<PairSeg>> per;
   auto emit = [&](int c, const T& t, int64_t k0, int64_t k1) {
@@ -330,7 +341,7 @@ void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairS
   const int64_t rem = ntile - rounds * C;
   if (rem > 0) {
     const int64_t p_lo = std::max<int64_t>(1, (kc + seg_cap - 1) / seg_cap);
-    const int64_t p_hi = std::max<int64_t>(p_lo, kc / (kc >= 8 * 64 ? 64 : min_chunks));
+    const int64_t p_hi = std::max<int64_t>(p_lo, kc / (kc >= 8 * 64 * chunk_scale ? 64 * chunk_scale : min_chunks));
     int64_t best_p = p_lo;
     double best = 1e30;
     for (int64_t p = p_lo; p <= p_hi; ++p) {
@@ -401,11 +412,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode2 = nullptr;
 
-template <int ELEM_BYTES, int FMT>
+template <int ELEM_BYTES, int FMT, int HALF>
 int launch_kernel2(int dev, const DeviceSchedule2& sched, const CUtensorMap& tm_x, const CUtensorMap& tm_g, int d,
                    cudaStream_t stream) {
   static std::atomic<bool> attr_done[64];
-  auto kernel = syrk_tc2_kernel<ELEM_BYTES, FMT>;
+  auto kernel = syrk_tc2_kernel<ELEM_BYTES, FMT, HALF>;
   if (dev >= 64 || !attr_done[dev].load(std::memory_order_acquire)) {
     VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     if (dev < 64) attr_done[dev].store(true, std::memory_order_release);
@@ -442,8 +453,12 @@ bool syrk_tc2_supported(int dtype, int d, int64_t ldx) {
 
 int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,
                     cudaStream_t stream) {
+  static const int half = [] {
+    const char* e = getenv("VLM_SYRK_HALF");
+    return e ? (atoi(e) != 0) : 0;
+  }();
   const int elem = (dtype == VLM_F32) ? 4 : 2;
-  const int bk = 128 / elem;
+  const int bk = (128 / elem) >> half;  // rows per pipeline stage = schedule chunk
   const int gc = 128 / elem;
   VLM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && ((ldx * elem) & 15) == 0, VLM_ERR_ALIGNMENT,
               "vlm_syrk_accum: x must be 16-byte aligned with a row pitch that is a multiple of 16 bytes");
@@ -473,7 +488,7 @@ int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, 
     if (it == g_sched2.end()) {
       std::vector<PairSeg> segs;
       std::vector<int> off;
-      build_pair_schedule(kc, d, nsm / 2, &segs, &off);
+      build_pair_schedule(kc, d, nsm / 2, &segs, &off, 1 << half);
       DeviceSchedule2 ds;
       ds.nclusters = (int)off.size() - 1;
       VLM_CUDA(cudaMalloc(&ds.d_segs, std::max<size_t>(1, segs.size()) * sizeof(PairSeg)));
@@ -494,7 +509,7 @@ int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, 
     // {column in group, row, column group}: strides row pitch and 128 bytes
     cuuint64_t gdim[3] = {(cuuint64_t)gc, (cuuint64_t)rows, (cuuint64_t)(d / gc)};
     cuuint64_t gstr[2] = {(cuuint64_t)ldx * elem, 128};
-    cuuint32_t box[3] = {(cuuint32_t)gc, (cuuint32_t)bk, (cuuint32_t)elem /* groups per 128-column block */};
+    cuuint32_t box[3] = {(cuuint32_t)gc, (cuuint32_t)bk, (cuuint32_t)elem /* groups per 128-column block */};  // bk rows per stage
     cuuint32_t estr[3] = {1, 1, 1};
     const CUtensorMapSwizzle swz = elem == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
     CUresult r = g_encode2(&tm_x, dt, 3, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -511,9 +526,14 @@ int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, 
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VLM_REQUIRE(r == CUDA_SUCCESS, VLM_ERR_DRIVER, "cuTensorMapEncodeTiled(G) failed: CUresult %d", (int)r);
   }
-  if (dtype == VLM_F32) return launch_kernel2<4, 2>(dev, sched, tm_x, tm_g, d, stream);
-  if (dtype == VLM_BF16) return launch_kernel2<2, 1>(dev, sched, tm_x, tm_g, d, stream);
-  return launch_kernel2<2, 0>(dev, sched, tm_x, tm_g, d, stream);
+  if (half) {
+    if (dtype == VLM_F32) return launch_kernel2<4, 2, 1>(dev, sched, tm_x, tm_g, d, stream);
+    if (dtype == VLM_BF16) return launch_kernel2<2, 1, 1>(dev, sched, tm_x, tm_g, d, stream);
+    return launch_kernel2<2, 0, 1>(dev, sched, tm_x, tm_g, d, stream);
+  }
+  if (dtype == VLM_F32) return launch_kernel2<4, 2, 0>(dev, sched, tm_x, tm_g, d, stream);
+  if (dtype == VLM_BF16) return launch_kernel2<2, 1, 0>(dev, sched, tm_x, tm_g, d, stream);
+  return launch_kernel2<2, 0, 0>(dev, sched, tm_x, tm_g, d, stream);
 }
 
 }  // namespace vlm
