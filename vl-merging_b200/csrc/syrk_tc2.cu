@@ -70,13 +70,6 @@ __device__ __forceinline__ void tma_load_3d_mcast(const CUtensorMap* tm, uint64_
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// L2 prefetch of one box (no shared memory involved): the later real load then hits L2
-__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
-                   reinterpret_cast<uint64_t>(tm)),
-               "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
 // tcgen05.commit arriving on the mbarrier at this smem offset in every CTA of `mask`
 __device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -90,19 +83,17 @@ struct PairSeg {
   int32_t sa, sb, k0, k1;
 };
 
-// HALF = 1 halves the rows per pipeline stage (16 fp32 / 32 16-bit rows) and doubles the stage count: same
-// bytes in flight, finer grain (7/8 instead of 3/4 of the buffer can be ahead of the tensor core).
-template <int ELEM_BYTES, int FMT, int HALF>
+template <int ELEM_BYTES, int FMT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
-                const PairSeg* __restrict__ segs, const int* __restrict__ seg_off, int d, int prefetch_dist) {
+                const PairSeg* __restrict__ segs, const int* __restrict__ seg_off, int d) {
   using G = Geo<ELEM_BYTES>;
-  constexpr int kRows = G::BK >> HALF;            // rows of X per pipeline stage
-  constexpr int kBlk = kBlockBytes >> HALF;       // bytes of one 128-column block per stage
-  constexpr int kBox = G::BOX_BYTES >> HALF;      // bytes of one column group per stage (= LBO)
-  constexpr int kNumMma = G::NUM_MMA >> HALF;
-  constexpr int kNStages = kStages << HALF;
-  constexpr int kStageB = 3 * kBlk;               // [B0][B1][A]
+  constexpr int kRows = G::BK;            // rows of X per pipeline stage
+  constexpr int kBlk = kBlockBytes;       // bytes of one 128-column block per stage
+  constexpr int kBox = G::BOX_BYTES;      // bytes of one column group per stage (= LBO of the UMMA descriptor)
+  constexpr int kNumMma = G::NUM_MMA;
+  constexpr int kNStages = kStages;
+  constexpr int kStageB = kStageBytes;    // [B0][B1][A]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
@@ -149,22 +140,6 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     // ===== TMA producer =====
     int stage = 0;
     uint32_t phase = 0;
-    // look-ahead cursor: prefetches into L2 the boxes this CTA will load `prefetch_dist` chunks from now
-    // (its own A block and the B block it multicasts), so that the real loads see L2-hit latency even on
-    // the first touch of a row panel
-    int ps = seg_begin, pk = (seg_begin < seg_end) ? segs[seg_begin].k0 : 0;
-    auto prefetch_next = [&]() {
-      if (ps >= seg_end) return;
-      const PairSeg p = segs[ps];
-      const int row = pk * kRows;
-      tma_prefetch_l2_3d(&tm_x, 0, row, (2 * p.sb + (int)rank) * G::GB);
-      if (p.sa != p.sb) tma_prefetch_l2_3d(&tm_x, 0, row, (2 * p.sa + (int)rank) * G::GB);
-      if (++pk >= p.k1) {
-        ++ps;
-        if (ps < seg_end) pk = segs[ps].k0;
-      }
-    };
-    for (int i = 0; i < prefetch_dist; ++i) prefetch_next();
     for (int s = seg_begin; s < seg_end; ++s) {
       const PairSeg seg = segs[s];
       const bool diag = seg.sa == seg.sb;
@@ -172,7 +147,6 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       const int b_group = (2 * seg.sb + (int)rank) * G::GB;       // ... of the B block this CTA fetches
       const uint32_t bytes = (diag ? 2u : 3u) * kBlk;             // both B blocks (+ own A block)
       for (int k = seg.k0; k < seg.k1; ++k) {
-        if (prefetch_dist > 0) prefetch_next();
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full[stage], bytes);
         uint8_t* sb = stage_base + stage * kStageB;
@@ -297,20 +271,15 @@ std::map<std::tuple<int, int64_t, int, int, int>, DeviceSchedule2> g_sched2;
 // A K range longer than seg_cap chunks is processed as consecutive segments of at most seg_cap chunks:
 // each ends with its own reduce-add into G (hidden behind the next segment's mainloop by the double-
 // buffered TMEM accumulator), which bounds the tensor core's truncating fp32 accumulation.
-// VLM_SYRK_SCHEDULE=panel selects the previous panel-major stream-K (kept for A/B measurements).
-void build_pair_schedule_panel(int64_t kc, int d, int nclusters_max, std::vector<PairSeg>* segs, std::vector<int>* off);
-
-// chunk_scale = schedule chunks per 128-byte-deep chunk (2 when the kernel runs half-height stages)
-void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairSeg>* segs, std::vector<int>* off,
-                         int chunk_scale = 1) {
-  if (const char* e = getenv("VLM_SYRK_SCHEDULE"))
-    if (!strcmp(e, "panel")) return build_pair_schedule_panel(kc, d, nclusters_max, segs, off);
+// Measured against the alternatives on the B200 (36928 x 3072 fp32): panel-major stream-K with chunk-granular
+// shares 672 TFLOP/s (many short segments whose 128 KB epilogues cannot hide), this schedule 753-758; an L2
+// look-ahead prefetch (cp.async.bulk.prefetch.tensor) cost 8 %, half-height stages x 8 cost 14 %.
+void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairSeg>* segs, std::vector<int>* off) {
   // chunks per accumulation: 4096 fp32 rows / 8192 16-bit rows.  Measured on the B200 with all-positive
   // activations 36928 x 3072: cap 128 / 256 / 512 / none -> rel. error 7.6e-4 / 7.8e-4 / 8.2e-4 / 1.0e-3 (fp32),
   // 2.2e-5 / 5.0e-5 / 8.8e-5 (bf16), at 742 / 753 / 766 / 779 TFLOP/s.
   int64_t seg_cap = 128;
   if (const char* e = getenv("VLM_SYRK_SEG_CHUNKS")) seg_cap = std::max(1, atoi(e));
-  seg_cap *= chunk_scale;
   const int nsb = (d + 255) / 256;
   struct T {
     int a, b;
@@ -319,7 +288,7 @@ void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairS
   for (int a = 0; a < nsb; ++a)
     for (int b = a; b < nsb; ++b) tiles.push_back({a, b});
   const int64_t ntile = (int64_t)tiles.size();
-  const int64_t min_chunks = 8 * chunk_scale;  // do not cut a K range below this: every piece pays a 128 KB epilogue per CTA
+  const int64_t min_chunks = 8;  // do not cut a K range below this: every piece pays a 128 KB epilogue per CTA
   const int C = nclusters_max;
   std::vector<std::vector<PairSeg>> per;
   auto emit = [&](int c, const T& t, int64_t k0, int64_t k1) {
@@ -341,7 +310,7 @@ void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairS
   const int64_t rem = ntile - rounds * C;
   if (rem > 0) {
     const int64_t p_lo = std::max<int64_t>(1, (kc + seg_cap - 1) / seg_cap);
-    const int64_t p_hi = std::max<int64_t>(p_lo, kc / (kc >= 8 * 64 * chunk_scale ? 64 * chunk_scale : min_chunks));
+    const int64_t p_hi = std::max<int64_t>(p_lo, kc / (kc >= 8 * 64 ? 64 : min_chunks));
     int64_t best_p = p_lo;
     double best = 1e30;
     for (int64_t p = p_lo; p <= p_hi; ++p) {
@@ -362,70 +331,21 @@ void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairS
   }
 }
 
-// Panel-major stream-K over super-tiles, one share per cluster (see build_syrk_schedule in syrk_tc.cu).
-void build_pair_schedule_panel(int64_t kc, int d, int nclusters_max, std::vector<PairSeg>* segs, std::vector<int>* off) {
-  int64_t panel_chunks = syrk_panel_chunks(d);
-  const int nsb = (d + 255) / 256;
-  struct T {
-    int a, b;
-  };
-  std::vector<T> tiles;
-  for (int a = 0; a < nsb; ++a)
-    for (int b = a; b < nsb; ++b) tiles.push_back({a, b});
-  const int64_t ntile = (int64_t)tiles.size();
-  const int64_t total = ntile * kc;
-  const int64_t min_cost = 16;  // chunks of a super-tile per cluster
-  const int ncl = (int)std::max<int64_t>(1, std::min<int64_t>(nclusters_max, total / min_cost));
-  const int64_t npanels = (kc + panel_chunks - 1) / panel_chunks;
-  std::vector<std::vector<PairSeg>> per(ncl);
-  for (int64_t p = 0; p < npanels; ++p) {
-    const int64_t k_lo = p * panel_chunks, k_hi = std::min(kc, k_lo + panel_chunks);
-    const int64_t panel_cost = ntile * (k_hi - k_lo);
-    const int rot = (int)((p * 37) % ncl);
-    int share = 0;
-    int64_t next_cut = panel_cost / ncl, pos = 0;
-    for (const T& t : tiles) {
-      int64_t k = k_lo;
-      while (k < k_hi) {
-        while (share < ncl - 1 && pos >= next_cut) {
-          ++share;
-          next_cut = panel_cost * (share + 1) / ncl;
-        }
-        const int64_t room = (share == ncl - 1) ? (k_hi - k) : (next_cut - pos);
-        const int64_t take = std::min(k_hi - k, std::max<int64_t>(room, 1));
-        per[(share + rot) % ncl].push_back({t.a, t.b, (int)k, (int)(k + take)});
-        k += take;
-        pos += take;
-      }
-    }
-  }
-  segs->clear();
-  off->assign(1, 0);
-  for (int c = 0; c < ncl; ++c) {
-    segs->insert(segs->end(), per[c].begin(), per[c].end());
-    off->push_back((int)segs->size());
-  }
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode2 = nullptr;
 
-template <int ELEM_BYTES, int FMT, int HALF>
+template <int ELEM_BYTES, int FMT>
 int launch_kernel2(int dev, const DeviceSchedule2& sched, const CUtensorMap& tm_x, const CUtensorMap& tm_g, int d,
                    cudaStream_t stream) {
   static std::atomic<bool> attr_done[64];
-  auto kernel = syrk_tc2_kernel<ELEM_BYTES, FMT, HALF>;
+  auto kernel = syrk_tc2_kernel<ELEM_BYTES, FMT>;
   if (dev >= 64 || !attr_done[dev].load(std::memory_order_acquire)) {
     VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     if (dev < 64) attr_done[dev].store(true, std::memory_order_release);
   }
-  static const int prefetch_dist = [] {
-    const char* e = getenv("VLM_SYRK_PREFETCH");
-    return e ? std::max(0, atoi(e)) : 0;
-  }();
-  kernel<<<2 * sched.nclusters, kThreads, kSmemBytes, stream>>>(tm_x, tm_g, sched.d_segs, sched.d_off, d, prefetch_dist);
+  kernel<<<2 * sched.nclusters, kThreads, kSmemBytes, stream>>>(tm_x, tm_g, sched.d_segs, sched.d_off, d);
   VLM_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -453,12 +373,8 @@ bool syrk_tc2_supported(int dtype, int d, int64_t ldx) {
 
 int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,
                     cudaStream_t stream) {
-  static const int half = [] {
-    const char* e = getenv("VLM_SYRK_HALF");
-    return e ? (atoi(e) != 0) : 0;
-  }();
   const int elem = (dtype == VLM_F32) ? 4 : 2;
-  const int bk = (128 / elem) >> half;  // rows per pipeline stage = schedule chunk
+  const int bk = 128 / elem;  // rows per pipeline stage = schedule chunk
   const int gc = 128 / elem;
   VLM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && ((ldx * elem) & 15) == 0, VLM_ERR_ALIGNMENT,
               "vlm_syrk_accum: x must be 16-byte aligned with a row pitch that is a multiple of 16 bytes");
@@ -488,7 +404,7 @@ int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, 
     if (it == g_sched2.end()) {
       std::vector<PairSeg> segs;
       std::vector<int> off;
-      build_pair_schedule(kc, d, nsm / 2, &segs, &off, 1 << half);
+      build_pair_schedule(kc, d, nsm / 2, &segs, &off);
       DeviceSchedule2 ds;
       ds.nclusters = (int)off.size() - 1;
       VLM_CUDA(cudaMalloc(&ds.d_segs, std::max<size_t>(1, segs.size()) * sizeof(PairSeg)));
@@ -509,7 +425,7 @@ int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, 
     // {column in group, row, column group}: strides row pitch and 128 bytes
     cuuint64_t gdim[3] = {(cuuint64_t)gc, (cuuint64_t)rows, (cuuint64_t)(d / gc)};
     cuuint64_t gstr[2] = {(cuuint64_t)ldx * elem, 128};
-    cuuint32_t box[3] = {(cuuint32_t)gc, (cuuint32_t)bk, (cuuint32_t)elem /* groups per 128-column block */};  // bk rows per stage
+    cuuint32_t box[3] = {(cuuint32_t)gc, (cuuint32_t)bk, (cuuint32_t)elem /* groups per 128-column block */};
     cuuint32_t estr[3] = {1, 1, 1};
     const CUtensorMapSwizzle swz = elem == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
     CUresult r = g_encode2(&tm_x, dt, 3, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -526,14 +442,9 @@ int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, 
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VLM_REQUIRE(r == CUDA_SUCCESS, VLM_ERR_DRIVER, "cuTensorMapEncodeTiled(G) failed: CUresult %d", (int)r);
   }
-  if (half) {
-    if (dtype == VLM_F32) return launch_kernel2<4, 2, 1>(dev, sched, tm_x, tm_g, d, stream);
-    if (dtype == VLM_BF16) return launch_kernel2<2, 1, 1>(dev, sched, tm_x, tm_g, d, stream);
-    return launch_kernel2<2, 0, 1>(dev, sched, tm_x, tm_g, d, stream);
-  }
-  if (dtype == VLM_F32) return launch_kernel2<4, 2, 0>(dev, sched, tm_x, tm_g, d, stream);
-  if (dtype == VLM_BF16) return launch_kernel2<2, 1, 0>(dev, sched, tm_x, tm_g, d, stream);
-  return launch_kernel2<2, 0, 0>(dev, sched, tm_x, tm_g, d, stream);
+  if (dtype == VLM_F32) return launch_kernel2<4, 2>(dev, sched, tm_x, tm_g, d, stream);
+  if (dtype == VLM_BF16) return launch_kernel2<2, 1>(dev, sched, tm_x, tm_g, d, stream);
+  return launch_kernel2<2, 0>(dev, sched, tm_x, tm_g, d, stream);
 }
 
 }  // namespace vlm
