@@ -2,14 +2,16 @@
 
   gram.GramCache                     RegMean Gram caching hook   (src/cache_gram_matrices.py:236-281,349)
   merge.merge_weights / sum_task_vectors / regmean / Merger      (src/vilt/modules/vilt_module.py:366-746)
+  checkpoint.modify_checkpoint_vlmo  checkpoint -> merge input (rel-pos table resize) (vilt_module.py:749-806)
   model.VLMo                         stock-torch multiway transformer the hooks hang on
   csrc/ + libvlmerge.so              sm_100a kernels behind the C ABI in include/vlmerge.h
 
 Importing the package never touches CUDA; the first compute call loads libvlmerge.so and fails
 loudly if it is missing (there is no CPU fallback).
 """
-from . import _lib, gram, merge, model, plan  # noqa: F401
+from . import _lib, checkpoint, gram, merge, model, plan  # noqa: F401
 from ._lib import VlmError, build  # noqa: F401
+from .checkpoint import load_checkpoint, modify_checkpoint_vlmo, save_checkpoint  # noqa: F401
 from .gram import GramCache  # noqa: F401
 from .merge import Merger, merge_weights, regmean, sum_task_vectors  # noqa: F401
 from .model import VLMo, init_synthetic_, synthetic_batch, vlmo_config  # noqa: F401

@@ -222,6 +222,12 @@ class VLMo(nn.Module):
         tidx[:, 0] = n_all - 2
         tidx[0, 0] = n_all - 1
         self.register_buffer("text_relative_position_index", tidx)
+        # joint text+image index (float, as the reference builds it, vilt_module.py:176-186); only the fused
+        # vl route reads it, but it is part of the checkpoint layout
+        t2i = torch.full((max_text, w * w + 1), float(n_img))
+        i2t = torch.full((w * w + 1, max_text), float(n_img + 1))
+        self.register_buffer("text_imag_relative_position_index",
+                             torch.cat((torch.cat((tidx.float(), t2i), 1), torch.cat((i2t, idx.float()), 1)), 0))
 
     # ---- forward (fine-tuning towers) ------------------------------------------------------------
     def _rel_pos_bias(self, index):
@@ -275,10 +281,11 @@ def init_synthetic_(model, seed=1):
     """Random-init stand-in for a trained checkpoint (there is no network for real ones): every tensor
     gets hash-uniform noise at the scale the reference initialises it with; LayerNorm weights ~ 1,
     layer-scale gammas ~ 0.1, relative position bias small."""
-    for n, (name, p) in enumerate(sorted(model.state_dict().items())):
-        if not p.dtype.is_floating_point:
-            continue
-        u = _hash_uniform(p.numel(), seed * 1000003 + n, device=p.device).reshape(p.shape)
+    import zlib
+
+    for name, p in model.named_parameters():  # parameters only: index buffers are functions of the config
+        # per-tensor stream keyed by the NAME, so adding or removing tensors never reshuffles the others
+        u = _hash_uniform(p.numel(), seed * 1000003 + zlib.crc32(name.encode()) % 999983, device=p.device).reshape(p.shape)
         if "norm" in name.lower() and name.endswith("weight"):
             p.copy_(1.0 + 0.2 * u)
         elif "gamma_" in name:
