@@ -310,6 +310,8 @@ def run_ours(args):
         regmean = bench_regmean(vlm, model, cfg, cache, dev, group, world, args)
         cache.reset()
 
+    irtr = bench_irtr(vlm, model, cfg, dev, group, world, args) if args.irtr else None
+
     out = None
     if rank == 0:
         out = {
@@ -323,7 +325,7 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (each step streams >2 GB of weights and activations)",
                        "allreduce_ms_in_timed_region": round(ar_ms, 3)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "merge": merge, "regmean": regmean, "gram_parity_rel_fro": parity,
+            "roofline": roofline, "merge": merge, "regmean": regmean, "irtr": irtr, "gram_parity_rel_fro": parity,
             "forward_variants": variants,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -410,6 +412,43 @@ def bench_merge(vlm, model, cfg, dev, group, world, rank, peaks, args):
         "e2e": {"value": round(nbytes / dt * 1e-9, 2), "unit": "GB/s", "seconds": round(dt, 4),
                 "h2d_bytes": stats.get("h2d_bytes"), "d2h_bytes": stats.get("d2h_bytes"), "bit_exact_vs_torch": bool(ok)},
     }
+
+
+def bench_irtr(vlm, model, cfg, dev, group, world, args, n_img=5000, per_img=5, bs=64):
+    """Config 4: modality arithmetic (lambda = 0.75, centre = a second synthetic ufo checkpoint) -> ufo model ->
+    IRTR forward over 5,000 synthetic images x 25,000 synthetic captions -> 5k x 25k similarity + recalls
+    (objectives.py:572-710), batches sharded over the ranks."""
+    import numpy as np
+
+    mcfg = dict(vlffn_start_layer_index=cfg["vlffn_start_layer_index"], only_activate_used_experts=True, sum_lambda=0.75,
+                loss_names={"irtr": 1, "vqa": 0, "nlvr2": 0})
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    ufo_cfg = dict(cfg, use_moe=False)
+    with torch.device(dev):
+        central = vlm.init_synthetic_(vlm.VLMo(ufo_cfg).eval(), seed=2)
+    t0 = time.perf_counter()
+    merged = vlm.sum_task_vectors(sd, mcfg, device=dev, num_layers=cfg["num_layers"], group=group,
+                                  central_weight=central.state_dict())
+    central.load_state_dict(merged, strict=False)   # reuse the module as the merged ufo model
+    torch.cuda.synchronize(dev)
+    t_merge = time.perf_counter() - t0
+    ufo = central
+    # synthetic eval set: 2 distinct image batches and 2 text batches cycled (content does not matter for timing)
+    ib = [vlm.synthetic_batch(bs, cfg, seed=900 + i, device=dev) for i in range(2)]
+    tb = [vlm.synthetic_batch(bs, cfg, seed=950 + i, device=dev, pad=True) for i in range(2)]
+    n_ib, n_tb = (n_img + bs - 1) // bs, (n_img * per_img + bs - 1) // bs
+    image_batches = [ib[i % 2] for i in range(n_ib)]
+    text_batches = [tb[i % 2] for i in range(n_tb)]
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    img, txt = vlm.irtr_features(ufo, image_batches, text_batches, autocast_dtype=torch.float16, group=group)
+    img, txt = img[:n_img], txt[: n_img * per_img]
+    scores, recalls = vlm.irtr_recall(img.float(), txt.float(), np.arange(n_img), np.arange(n_img * per_img) // per_img)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    return {"merge_seconds": round(t_merge, 4), "eval_seconds": round(dt, 3), "images": n_img, "captions": n_img * per_img,
+            "scores_shape": list(scores.shape), "forwards_per_sec": round((n_img + n_img * per_img) / dt, 1),
+            "autocast": "fp16 (as objectives.py:657,669)", "recalls": [round(float(r), 5) for r in recalls]}
 
 
 def bench_regmean(vlm, model, cfg, cache, dev, group, world, args):
@@ -552,6 +591,8 @@ def main():
                     help="attention of the stock-torch forward: the reference's explicit softmax, or torch SDPA")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra (informational) forward variants")
     ap.add_argument("--no-regmean", action="store_true")
+    ap.add_argument("--irtr", action="store_true",
+                    help="also run config 4: modality-arithmetic merge + IRTR forward over 5k synthetic images x 25k captions")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true",
                     help="for ncu launch lists: run exactly --warmup + --steps calibration steps and exit (no JSON line)")

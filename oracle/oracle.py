@@ -213,3 +213,17 @@ def reference_hook_torch(store):
         store[module.module_name] += torch.matmul(flat.T, flat).detach().cpu()
 
     return hook_gram_input
+
+
+def irtr_recall(img_feats, txt_feats, iids, tiids):
+    """src/vilt/modules/objectives.py:684-710 in numpy: scores = img @ txt.T; recall@{1,5,10} both directions.
+    Returns (scores, (ir_r1, ir_r5, ir_r10, tr_r1, tr_r5, tr_r10))."""
+    scores = np.asarray(img_feats) @ np.asarray(txt_feats).T
+    iids, tiids = np.asarray(iids), np.asarray(tiids)
+    res = {}
+    for k in (1, 5, 10):
+        top = np.argsort(-scores, axis=1, kind="stable")[:, :k]           # per image: best captions (:688-690)
+        res[f"tr_r{k}"] = (iids[:, None] == tiids[top]).max(axis=1).astype(np.float32).mean()
+        top = np.argsort(-scores, axis=0, kind="stable")[:k, :]           # per caption: best images (:699-701)
+        res[f"ir_r{k}"] = (tiids[None, :] == iids[top]).max(axis=0).astype(np.float32).mean()
+    return scores, (res["ir_r1"], res["ir_r5"], res["ir_r10"], res["tr_r1"], res["tr_r5"], res["tr_r10"])

@@ -39,12 +39,20 @@ def _worker(rank, world, port, ret):
                     scaling_for_non_diag=0.9, loss_names={"irtr": 1.0, "vqa": 0, "nlvr2": 0})
         merged = vlm.merge_weights(sd, mcfg, group=dist.group.WORLD)
         rm = vlm.regmean(sd, mcfg, gram_matrices=grams, group=dist.group.WORLD)
+        ufo = vlm.VLMo(vlm.vlmo_config("tiny", use_moe=False)).eval().cuda()
+        ufo.load_state_dict(merged, strict=False)
+        ib = [vlm.synthetic_batch(3, cfg, seed=70 + i, device="cuda") for i in range(3)]
+        tb = [vlm.synthetic_batch(4, cfg, seed=80 + i, device="cuda", pad=True) for i in range(5)]
+        img_f, txt_f = vlm.irtr_features(ufo, ib, tb, group=dist.group.WORLD)     # batches sharded over the ranks
+        img_1, txt_1 = vlm.irtr_features(ufo, ib, tb)                              # every batch on this rank
+        irtr_err = max((img_f - img_1).abs().max().item(), (txt_f - txt_1).abs().max().item())
         pick = ["transformer.blocks.0.attn.qkv.weight", "transformer.blocks.11.mlp.fc2.weight", "transformer.blocks.4.norm2.bias"]
         ret[rank] = {
             "grams": {k: grams[k].numpy() for k in ("transformer.blocks.0.attn.v", "transformer.blocks.7.mlp.l.fc2")},
             "n_grams": len(grams),
             "merged": {k: merged[k].cpu().numpy() for k in pick},
             "regmean": {k: rm[k].cpu().numpy() for k in pick},
+            "irtr_err": irtr_err, "irtr_shapes": (tuple(img_f.shape), tuple(txt_f.shape)),
         }
     finally:
         dist.destroy_process_group()
@@ -61,6 +69,7 @@ def test_two_rank_calibration_and_sharded_merge():
     mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
     r0, r1 = ret[0], ret[1]
     assert r0["n_grams"] == r1["n_grams"] == 96
+    assert r0["irtr_shapes"] == ((9, 192), (20, 192)) and max(r0["irtr_err"], r1["irtr_err"]) < 1e-5
     # single-process oracle for the reduced result: one cache over both shards
     cfg = vlm.vlmo_config("tiny")
     model = vlm.init_synthetic_(vlm.VLMo(cfg).eval(), seed=1).cuda()

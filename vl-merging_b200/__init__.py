@@ -9,10 +9,11 @@
 Importing the package never touches CUDA; the first compute call loads libvlmerge.so and fails
 loudly if it is missing (there is no CPU fallback).
 """
-from . import _lib, checkpoint, gram, merge, model, plan  # noqa: F401
+from . import _lib, checkpoint, gram, irtr, merge, model, plan  # noqa: F401
 from ._lib import VlmError, build  # noqa: F401
 from .checkpoint import load_checkpoint, modify_checkpoint_vlmo, save_checkpoint  # noqa: F401
 from .gram import GramCache  # noqa: F401
+from .irtr import irtr_features, irtr_recall  # noqa: F401
 from .merge import Merger, merge_weights, regmean, sum_task_vectors  # noqa: F401
 from .model import VLMo, init_synthetic_, synthetic_batch, vlmo_config  # noqa: F401
 
