@@ -51,7 +51,9 @@ regmean_rhs_kernel(const float* __restrict__ w, int M, int K, int64_t ldw, const
                    double alpha, double oma, double* __restrict__ acc, int64_t ldacc, int accumulate) {
   __shared__ double sa[2][BM][BKK + 1];  // W tile, widened
   __shared__ double sb[2][BKK][BN + 1];  // Ghat tile
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // blockIdx.x walks the rows of W (fast), blockIdx.y the columns of G: blocks that run together share one
+  // 16 x 64 column strip of G per K step, so G (up to 67 MB fp32 for in_f = 4096) streams from HBM once
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int N = K;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
@@ -172,7 +174,7 @@ extern "C" int vlm_regmean_rhs(const float* w, int out_f, int in_f, int64_t ldw,
               VLM_ERR_INVALID_ARG, "vlm_regmean_rhs: bad arguments");
   VLM_REQUIRE(g_dtype == VLM_F64 || g_dtype == VLM_F32, VLM_ERR_INVALID_ARG,
               "vlm_regmean_rhs: g_dtype must be VLM_F64 or VLM_F32");
-  dim3 grid((in_f + BN - 1) / BN, (out_f + BM - 1) / BM);
+  dim3 grid((out_f + BM - 1) / BM, (in_f + BN - 1) / BN);
   auto s = static_cast<cudaStream_t>(stream);
   if (g_dtype == VLM_F64)
     regmean_rhs_kernel<double><<<grid, 128, 0, s>>>(w, out_f, in_f, ldw, static_cast<const double*>(g), ldg, alpha,

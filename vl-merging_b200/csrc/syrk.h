@@ -29,9 +29,18 @@ void build_syrk_schedule(int64_t kc, int d, int nsm, std::vector<SyrkSeg>* segs,
 
 int syrk_tc_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,
                    cudaStream_t stream);
+// One unit of work of a CLUSTER (CTA-pair kernels): super-tile (sa, sb) in 256-column units, row chunks [k0, k1).
+struct PairSeg {
+  int32_t sa, sb, k0, k1;
+};
+void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairSeg>* segs, std::vector<int>* off);
+
 // second generation: CTA pairs + TMA multicast + 3-D boxes (syrk_tc2.cu); needs whole 128-byte column groups
 bool syrk_tc2_supported(int dtype, int d, int64_t ldx);
 int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,
+                    cudaStream_t stream);
+// third generation: one tcgen05.mma.cta_group::2 per K step for the pair (syrk_tc3.cu); same preconditions
+int syrk_tc3_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,
                     cudaStream_t stream);
 void build_syrk_pair_schedule_host(int64_t kc, int d, int nsm, std::vector<int32_t>* flat, std::vector<int>* off);
 int syrk_simt_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,

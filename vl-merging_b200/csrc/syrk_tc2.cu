@@ -78,11 +78,6 @@ __device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t mask) {
                : "memory");
 }
 
-// One unit of work of a CLUSTER: super-tile (sa, sb) in 256-column units, row chunks [k0, k1).
-struct PairSeg {
-  int32_t sa, sb, k0, k1;
-};
-
 template <int ELEM_BYTES, int FMT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
@@ -259,6 +254,28 @@ struct DeviceSchedule2 {
 std::mutex g_mu2;
 std::map<std::tuple<int, int64_t, int, int, int>, DeviceSchedule2> g_sched2;
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode2 = nullptr;
+
+template <int ELEM_BYTES, int FMT>
+int launch_kernel2(int dev, const DeviceSchedule2& sched, const CUtensorMap& tm_x, const CUtensorMap& tm_g, int d,
+                   cudaStream_t stream) {
+  static std::atomic<bool> attr_done[64];
+  auto kernel = syrk_tc2_kernel<ELEM_BYTES, FMT>;
+  if (dev >= 64 || !attr_done[dev].load(std::memory_order_acquire)) {
+    VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    if (dev < 64) attr_done[dev].store(true, std::memory_order_release);
+  }
+  kernel<<<2 * sched.nclusters, kThreads, kSmemBytes, stream>>>(tm_x, tm_g, sched.d_segs, sched.d_off, d);
+  VLM_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace
+
 // Work decomposition for the CTA-pair kernel: K-ALIGNED tile ownership.
 //
 // Every cluster sweeps the rows of X from the top for "its" super-tile, so at any moment all clusters read
@@ -330,28 +347,6 @@ void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairS
     off->push_back((int)segs->size());
   }
 }
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn g_encode2 = nullptr;
-
-template <int ELEM_BYTES, int FMT>
-int launch_kernel2(int dev, const DeviceSchedule2& sched, const CUtensorMap& tm_x, const CUtensorMap& tm_g, int d,
-                   cudaStream_t stream) {
-  static std::atomic<bool> attr_done[64];
-  auto kernel = syrk_tc2_kernel<ELEM_BYTES, FMT>;
-  if (dev >= 64 || !attr_done[dev].load(std::memory_order_acquire)) {
-    VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    if (dev < 64) attr_done[dev].store(true, std::memory_order_release);
-  }
-  kernel<<<2 * sched.nclusters, kThreads, kSmemBytes, stream>>>(tm_x, tm_g, sched.d_segs, sched.d_off, d);
-  VLM_CUDA(cudaGetLastError());
-  count_launch();
-  return 0;
-}
-
-}  // namespace
 
 // Host view for the CPU tests: segments as {super_row, super_col, k0, k1} per cluster.
 void build_syrk_pair_schedule_host(int64_t kc, int d, int nsm, std::vector<int32_t>* flat, std::vector<int>* off) {
