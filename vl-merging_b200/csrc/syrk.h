@@ -39,9 +39,6 @@ void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairS
 bool syrk_tc2_supported(int dtype, int d, int64_t ldx);
 int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,
                     cudaStream_t stream);
-// third generation: one tcgen05.mma.cta_group::2 per K step for the pair (syrk_tc3.cu); same preconditions
-int syrk_tc3_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,
-                    cudaStream_t stream);
 void build_syrk_pair_schedule_host(int64_t kc, int d, int nsm, std::vector<int32_t>* flat, std::vector<int>* off);
 int syrk_simt_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,
                      cudaStream_t stream);

@@ -290,7 +290,10 @@ int launch_kernel2(int dev, const DeviceSchedule2& sched, const CUtensorMap& tm_
 // buffered TMEM accumulator), which bounds the tensor core's truncating fp32 accumulation.
 // Measured against the alternatives on the B200 (36928 x 3072 fp32): panel-major stream-K with chunk-granular
 // shares 672 TFLOP/s (many short segments whose 128 KB epilogues cannot hide), this schedule 753-758; an L2
-// look-ahead prefetch (cp.async.bulk.prefetch.tensor) cost 8 %, half-height stages x 8 cost 14 %.
+// look-ahead prefetch (cp.async.bulk.prefetch.tensor) cost 8 %, half-height stages x 8 cost 14 %.  A variant
+// issuing ONE tcgen05.mma.cta_group::2 (M = 256) per K step for the pair (32 KB stages x 6, no multicast) was
+// bit-for-bit as accurate but ran at exactly half the speed (380 TFLOP/s, tensor pipe 37 % active in ncu) with
+// these MN-major operands, so the pair keeps two independent cta_group::1 instruction streams.
 void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairSeg>* segs, std::vector<int>* off) {
   // chunks per accumulation: 4096 fp32 rows / 8192 16-bit rows.  Measured on the B200 with all-positive
   // activations 36928 x 3072: cap 128 / 256 / 512 / none -> rel. error 7.6e-4 / 7.8e-4 / 8.2e-4 / 1.0e-3 (fp32),
