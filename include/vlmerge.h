@@ -58,6 +58,21 @@ uint64_t    vlm_launch_count(void);
 int vlm_syrk_accum(const void* x, int dtype, int64_t rows, int d, int64_t ldx,
                    float* g, int64_t ldg, void* stream);
 
+/* Several independent vlm_syrk_accum problems of the same dtype in ONE launch (e.g. the 48 small Grams of the
+ * text tower of one forward, which are launch-bound one by one).  Same contract per problem; the activations
+ * must stay alive and unmodified until `stream` has run the launch.  Problems TMA cannot address, or whose
+ * column count is not a whole number of 128-byte groups, are issued as individual launches. */
+typedef struct {
+  const void* x;
+  int64_t     rows;
+  int64_t     ldx;
+  float*      g;
+  int64_t     ldg;
+  int32_t     d;
+  int32_t     reserved;
+} vlm_syrk_problem;
+int vlm_syrk_accum_batch(const vlm_syrk_problem* probs_host, int n, int dtype, void* stream);
+
 /* Same contract on CUDA cores (fp32 FMA), any alignment.  Debug oracle on the device and the
  * path for activations TMA cannot address. */
 int vlm_syrk_accum_simt(const void* x, int dtype, int64_t rows, int d, int64_t ldx,

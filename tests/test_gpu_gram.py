@@ -112,3 +112,39 @@ def test_registration_and_reference_file_format(tmp_path):
     assert loaded["transformer.blocks.11.mlp.l.fc2"].shape == (768, 768)
     assert not any(".vl" in k for k in loaded)      # vl experts never run in IRTR calibration
     assert loaded["missing-key"] == 0.0             # still a defaultdict(float), like the reference's
+
+
+def test_batched_launch_matches_individual_launches():
+    """vlm_syrk_accum_batch through GramCache(defer_rows=...): mixed shapes in one grid, incl. a column count that
+    is not a whole number of 128-byte groups (issued individually) and two accumulations into the same Gram."""
+    shapes = [(2560, 768), (2560, 3072), (40, 768), (333, 200), (1000, 1024), (2560, 768)]
+    names = ["a", "b", "c", "odd", "e", "a"]
+    xs = [_x(sh, torch.float32, 100 + i, positive=(i % 2 == 1)).cuda() for i, sh in enumerate(shapes)]
+    now, later = vlm.GramCache(), vlm.GramCache(defer_rows=4096)
+    for n, x in zip(names, xs):
+        now.accumulate(n, x)
+        later.accumulate(n, x)
+    assert len(later._pending) == len(shapes)
+    later.flush()
+    assert not later._pending
+    for n in set(names):
+        a, b = now.gram(n).double(), later.gram(n).double()
+        assert ((a - b).norm() / a.norm()).item() < 1e-6, n      # same arithmetic, different reduce-add order
+    xd = torch.cat([xs[0], xs[5]]).double()
+    ref = xd.T @ xd
+    assert ((later.gram("a").double() - ref).norm() / ref.norm()).item() < 1e-3
+
+
+def test_deferred_hooks_flush_after_each_forward():
+    cfg = vlm.vlmo_config("tiny")
+    model = vlm.init_synthetic_(vlm.VLMo(cfg).eval(), seed=1).cuda()
+    a, b = vlm.GramCache(), vlm.GramCache(defer_rows=100000)   # defer everything
+    a.register(model)
+    b.register(model)
+    with torch.no_grad():
+        model(vlm.synthetic_batch(2, cfg, seed=3, device="cuda", pad=True))
+    assert not b._pending                                      # flushed by the forward hook on the model
+    ga, gb = a.state_dict(), b.state_dict()
+    assert list(ga) == list(gb) and len(gb) == 96
+    worst = max(((ga[k] - gb[k]).norm() / ga[k].norm()).item() for k in ga)
+    assert worst < 1e-6, worst

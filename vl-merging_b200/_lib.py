@@ -29,6 +29,19 @@ class MergeSeg(ctypes.Structure):
     ]
 
 
+class SyrkProblem(ctypes.Structure):
+    """vlm_syrk_problem"""
+    _fields_ = [
+        ("x", c_void_p),
+        ("rows", c_int64),
+        ("ldx", c_int64),
+        ("g", c_void_p),
+        ("ldg", c_int64),
+        ("d", c_int32),
+        ("reserved", c_int32),
+    ]
+
+
 class VlmError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libvlmerge error {code}: {msg}")
@@ -41,6 +54,7 @@ SIGNATURES = {
     "vlm_last_error": (c_char_p, []),
     "vlm_launch_count": (c_uint64, []),
     "vlm_syrk_accum": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_int64, c_void_p]),
+    "vlm_syrk_accum_batch": (c_int, [POINTER(SyrkProblem), c_int, c_int, c_void_p]),
     "vlm_syrk_accum_simt": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_int64, c_void_p]),
     "vlm_sym_finalize": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p]),
     "vlm_syrk_schedule_host": (c_int, [c_int64, c_int, c_int, c_int, POINTER(c_int32), c_int, POINTER(c_int32),

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "syrk.h"
@@ -88,6 +89,32 @@ extern "C" int vlm_syrk_accum(const void* x, int dtype, int64_t rows, int d, int
   if (variant == 2 && syrk_tc2_supported(dtype, d, ldx))
     return syrk_tc2_launch(x, dtype, rows, d, ldx, g, ldg, static_cast<cudaStream_t>(stream));
   return syrk_tc_launch(x, dtype, rows, d, ldx, g, ldg, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vlm_syrk_accum_simt(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,
+                                   void* stream);
+
+extern "C" int vlm_syrk_accum_batch(const vlm_syrk_problem* probs, int n, int dtype, void* stream) {
+  VLM_REQUIRE(n >= 0 && (probs != nullptr || n == 0), VLM_ERR_INVALID_ARG, "vlm_syrk_accum_batch: bad arguments");
+  if (n == 0) return 0;
+  if (int rc = require_sm100()) return rc;
+  std::vector<vlm_syrk_problem> grouped;
+  for (int p = 0; p < n; ++p) {
+    const vlm_syrk_problem& q = probs[p];
+    if (int rc = check_syrk_args("vlm_syrk_accum_batch", q.x, dtype, q.rows, q.d, q.ldx, q.g, q.ldg)) return rc;
+    if (q.rows == 0) continue;
+    const int elem = dtype == VLM_F32 ? 4 : 2;
+    const bool tma_ok = (reinterpret_cast<uintptr_t>(q.x) & 15) == 0 && ((q.ldx * elem) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(q.g) & 15) == 0 && (q.ldg & 3) == 0;
+    if (tma_ok && syrk_tc2_supported(dtype, q.d, q.ldx)) {
+      grouped.push_back(q);
+    } else if (int rc = tma_ok ? vlm_syrk_accum(q.x, dtype, q.rows, q.d, q.ldx, q.g, q.ldg, stream)
+                               : vlm_syrk_accum_simt(q.x, dtype, q.rows, q.d, q.ldx, q.g, q.ldg, stream)) {
+      return rc;
+    }
+  }
+  if (grouped.empty()) return 0;
+  return syrk_tc2_batch_launch(grouped.data(), (int)grouped.size(), dtype, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vlm_syrk_accum_simt(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,

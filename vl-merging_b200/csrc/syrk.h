@@ -7,6 +7,8 @@
 
 #include <cuda_runtime.h>
 
+#include "../../include/vlmerge.h"
+
 namespace vlm {
 
 // One unit of work of the tcgen05 SYRK kernel: output tile rows [col_a, col_a+128), columns
@@ -39,6 +41,8 @@ void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairS
 bool syrk_tc2_supported(int dtype, int d, int64_t ldx);
 int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,
                     cudaStream_t stream);
+// several independent problems (same dtype) in one grid; every problem must satisfy syrk_tc2_supported
+int syrk_tc2_batch_launch(const vlm_syrk_problem* probs, int n, int dtype, cudaStream_t stream);
 void build_syrk_pair_schedule_host(int64_t kc, int d, int nsm, std::vector<int32_t>* flat, std::vector<int>* off);
 int syrk_simt_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,
                      cudaStream_t stream);

@@ -23,9 +23,11 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -78,11 +80,35 @@ __device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t mask) {
                : "memory");
 }
 
-template <int ELEM_BYTES, int FMT>
+// One unit of work of a cluster in a BATCHED launch (several independent Gram problems in one grid): as PairSeg,
+// plus which problem it belongs to (index into the tensor-map array) and that problem's column count.
+struct BatchSeg {
+  int32_t sa, sb, k0, k1, pid, d;
+};
+__device__ __forceinline__ void tensormap_acquire(const CUtensorMap* tm) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+// BATCH = false: one problem, tensor maps in kernel parameters.  BATCH = true: the segments of several problems
+// (e.g. all Grams of the text tower of one forward) share the grid; tensor maps live in global memory (`maps`:
+// [2*pid] = X, [2*pid+1] = G), written by the host before the launch.
+template <int ELEM_BYTES, int FMT, bool BATCH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
-                const PairSeg* __restrict__ segs, const int* __restrict__ seg_off, int d) {
+syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_g1,
+                const CUtensorMap* __restrict__ maps, const void* __restrict__ segs_raw,
+                const int* __restrict__ seg_off, int d1) {
   using G = Geo<ELEM_BYTES>;
+  using Seg = typename std::conditional<BATCH, BatchSeg, PairSeg>::type;
+  const Seg* __restrict__ segs = static_cast<const Seg*>(segs_raw);
+  auto map_x = [&](const Seg& sg) -> const CUtensorMap* {
+    if constexpr (BATCH) return maps + 2 * sg.pid; else return &tm_x1;
+  };
+  auto map_g = [&](const Seg& sg) -> const CUtensorMap* {
+    if constexpr (BATCH) return maps + 2 * sg.pid + 1; else return &tm_g1;
+  };
+  auto cols_of = [&](const Seg& sg) -> int {
+    if constexpr (BATCH) return sg.d; else return d1;
+  };
   constexpr int kRows = G::BK;            // rows of X per pipeline stage
   constexpr int kBlk = kBlockBytes;       // bytes of one 128-column block per stage
   constexpr int kBox = G::BOX_BYTES;      // bytes of one column group per stage (= LBO of the UMMA descriptor)
@@ -107,9 +133,9 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   const int seg_begin = seg_off[cluster_id];
   const int seg_end = seg_off[cluster_id + 1];
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_x);
-    tma_prefetch_desc(&tm_g);
+  if (!BATCH && warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x1);
+    tma_prefetch_desc(&tm_g1);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kNStages; ++i) {
@@ -135,8 +161,16 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     // ===== TMA producer =====
     int stage = 0;
     uint32_t phase = 0;
+    int cur_pid = -1;
     for (int s = seg_begin; s < seg_end; ++s) {
-      const PairSeg seg = segs[s];
+      const Seg seg = segs[s];
+      const CUtensorMap* tm_x = map_x(seg);
+      if constexpr (BATCH) {
+        if (seg.pid != cur_pid) {
+          tensormap_acquire(tm_x);
+          cur_pid = seg.pid;
+        }
+      }
       const bool diag = seg.sa == seg.sb;
       const int a_group = (2 * seg.sa + (int)rank) * G::GB;       // first column group of this CTA's A block
       const int b_group = (2 * seg.sb + (int)rank) * G::GB;       // ... of the B block this CTA fetches
@@ -146,8 +180,8 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         mbar_arrive_expect_tx(&full[stage], bytes);
         uint8_t* sb = stage_base + stage * kStageB;
         const int row = k * kRows;
-        tma_load_3d_mcast(&tm_x, &full[stage], sb + rank * kBlk, 0, row, b_group, (uint16_t)0x3);
-        if (!diag) tma_load_3d(&tm_x, &full[stage], sb + 2 * kBlk, 0, row, a_group);
+        tma_load_3d_mcast(tm_x, &full[stage], sb + rank * kBlk, 0, row, b_group, (uint16_t)0x3);
+        if (!diag) tma_load_3d(tm_x, &full[stage], sb + 2 * kBlk, 0, row, a_group);
         if (++stage == kNStages) {
           stage = 0;
           phase ^= 1;
@@ -161,7 +195,7 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int s = seg_begin; s < seg_end; ++s) {
-      const PairSeg seg = segs[s];
+      const Seg seg = segs[s];
       const bool diag = seg.sa == seg.sb;
       // diagonal super-tile: CTA 1 forms only its diagonal block (B block 1, N = 128)
       const int n_off = (diag && rank == 1) ? 1 : 0;
@@ -200,8 +234,17 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t slab_counter = 0;
+    int cur_pid = -1;
     for (int s = seg_begin; s < seg_end; ++s) {
-      const PairSeg seg = segs[s];
+      const Seg seg = segs[s];
+      const CUtensorMap* tm_g = map_g(seg);
+      const int d = cols_of(seg);
+      if constexpr (BATCH) {
+        if (epi_tid == 0 && seg.pid != cur_pid) {
+          tensormap_acquire(tm_g);
+          cur_pid = seg.pid;
+        }
+      }
       const bool diag = seg.sa == seg.sb;
       const int n_off = (diag && rank == 1) ? 1 : 0;
       const int w = 2 - n_off;
@@ -210,10 +253,16 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int nslab = (row0 < d) ? min(4 * w, (d - col0 + 31) / 32) : 0;
+      // After this CTA's LAST segment the pipeline stages are dead (every load was consumed by the MMAs that
+      // tfull just reported complete, in this CTA and — for the multicast halves — in the peer), so each slab
+      // gets its own 16 KB staging slot there and no slab waits for an earlier TMA store to drain.
+      const bool last = (s == seg_end - 1);
       for (int sl = 0; sl < nslab; ++sl) {
-        uint8_t* buf = staging + (slab_counter & 1) * kStagingBytes;
-        if (epi_tid == 0) bulk_wait_group_read<1>();
-        named_bar_sync(1, 128);
+        uint8_t* buf = last ? stage_base + sl * kStagingBytes : staging + (slab_counter & 1) * kStagingBytes;
+        if (!last) {
+          if (epi_tid == 0) bulk_wait_group_read<1>();
+          named_bar_sync(1, 128);
+        }
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols + sl * 32, v);
         tmem_ld_wait();
@@ -228,7 +277,7 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (epi_tid == 0) {
-          tma_reduce_add_2d(&tm_g, buf, col0 + sl * 32, row0);
+          tma_reduce_add_2d(tm_g, buf, col0 + sl * 32, row0);
           bulk_commit_group();
         }
         ++slab_counter;
@@ -259,16 +308,77 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode2 = nullptr;
 
+int ensure_encode() {
+  std::lock_guard<std::mutex> lk(g_mu2);
+  if (!g_encode2) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    VLM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    VLM_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, VLM_ERR_DRIVER,
+                "cuTensorMapEncodeTiled not available from the driver");
+    g_encode2 = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  return 0;
+}
+
+// X as a 3-D tensor {column in group, row, column group} (strides: row pitch, 128 bytes); G as a 2-D fp32 tensor
+int encode_maps(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg, CUtensorMap* tm_x,
+                CUtensorMap* tm_g) {
+  const int elem = (dtype == VLM_F32) ? 4 : 2;
+  const int bk = 128 / elem, gc = 128 / elem;
+  {
+    const CUtensorMapDataType dt = dtype == VLM_F32    ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                   : dtype == VLM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                       : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    cuuint64_t gdim[3] = {(cuuint64_t)gc, (cuuint64_t)rows, (cuuint64_t)(d / gc)};
+    cuuint64_t gstr[2] = {(cuuint64_t)ldx * elem, 128};
+    cuuint32_t box[3] = {(cuuint32_t)gc, (cuuint32_t)bk, (cuuint32_t)elem /* groups per 128-column block */};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapSwizzle swz = elem == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+    CUresult r = g_encode2(tm_x, dt, 3, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VLM_REQUIRE(r == CUDA_SUCCESS, VLM_ERR_DRIVER, "cuTensorMapEncodeTiled(X, 3-D) failed: CUresult %d", (int)r);
+  }
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)d};
+    cuuint64_t gstr[1] = {(cuuint64_t)ldg * 4};
+    cuuint32_t box[2] = {32, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode2(tm_g, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g, gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VLM_REQUIRE(r == CUDA_SUCCESS, VLM_ERR_DRIVER, "cuTensorMapEncodeTiled(G) failed: CUresult %d", (int)r);
+  }
+  return 0;
+}
+
+int check_alignment(const void* x, int elem, int64_t rows, int64_t ldx, const float* g, int64_t ldg) {
+  VLM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && ((ldx * elem) & 15) == 0, VLM_ERR_ALIGNMENT,
+              "vlm_syrk_accum: x must be 16-byte aligned with a row pitch that is a multiple of 16 bytes");
+  VLM_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0 && (ldg & 3) == 0, VLM_ERR_ALIGNMENT,
+              "vlm_syrk_accum: g must be 16-byte aligned with ldg %% 4 == 0");
+  VLM_REQUIRE(rows < (int64_t)1 << 31, VLM_ERR_INVALID_ARG, "vlm_syrk_accum: rows too large");
+  return 0;
+}
+
+// device scratch for batched launches: a small ring per (device, stream); reuse is ordered by the stream itself
+struct Scratch {
+  void* ptr[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t cap[4] = {0, 0, 0, 0};
+  int next = 0;
+};
+std::map<std::pair<int, cudaStream_t>, Scratch> g_scratch;
+
 template <int ELEM_BYTES, int FMT>
 int launch_kernel2(int dev, const DeviceSchedule2& sched, const CUtensorMap& tm_x, const CUtensorMap& tm_g, int d,
                    cudaStream_t stream) {
   static std::atomic<bool> attr_done[64];
-  auto kernel = syrk_tc2_kernel<ELEM_BYTES, FMT>;
+  auto kernel = syrk_tc2_kernel<ELEM_BYTES, FMT, false>;
   if (dev >= 64 || !attr_done[dev].load(std::memory_order_acquire)) {
     VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     if (dev < 64) attr_done[dev].store(true, std::memory_order_release);
   }
-  kernel<<<2 * sched.nclusters, kThreads, kSmemBytes, stream>>>(tm_x, tm_g, sched.d_segs, sched.d_off, d);
+  kernel<<<2 * sched.nclusters, kThreads, kSmemBytes, stream>>>(tm_x, tm_g, nullptr, sched.d_segs, sched.d_off, d);
   VLM_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -373,26 +483,11 @@ int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, 
                     cudaStream_t stream) {
   const int elem = (dtype == VLM_F32) ? 4 : 2;
   const int bk = 128 / elem;  // rows per pipeline stage = schedule chunk
-  const int gc = 128 / elem;
-  VLM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && ((ldx * elem) & 15) == 0, VLM_ERR_ALIGNMENT,
-              "vlm_syrk_accum: x must be 16-byte aligned with a row pitch that is a multiple of 16 bytes");
-  VLM_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0 && (ldg & 3) == 0, VLM_ERR_ALIGNMENT,
-              "vlm_syrk_accum: g must be 16-byte aligned with ldg %% 4 == 0");
-  VLM_REQUIRE(rows < (int64_t)1 << 31, VLM_ERR_INVALID_ARG, "vlm_syrk_accum: rows too large");
+  if (int rc = check_alignment(x, elem, rows, ldx, g, ldg)) return rc;
   int dev = 0, nsm = 0;
   VLM_CUDA(cudaGetDevice(&dev));
   if (int rc = device_sm_count(&nsm)) return rc;
-  {
-    std::lock_guard<std::mutex> lk(g_mu2);
-    if (!g_encode2) {
-      void* fn = nullptr;
-      cudaDriverEntryPointQueryResult qres;
-      VLM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-      VLM_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, VLM_ERR_DRIVER,
-                  "cuTensorMapEncodeTiled not available from the driver");
-      g_encode2 = reinterpret_cast<EncodeTiledFn>(fn);
-    }
-  }
+  if (int rc = ensure_encode()) return rc;
   const int64_t kc = (rows + bk - 1) / bk;
   DeviceSchedule2 sched;
   {
@@ -416,33 +511,93 @@ int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, 
   }
 
   CUtensorMap tm_x, tm_g;
-  {
-    const CUtensorMapDataType dt = dtype == VLM_F32    ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
-                                   : dtype == VLM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
-                                                       : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    // {column in group, row, column group}: strides row pitch and 128 bytes
-    cuuint64_t gdim[3] = {(cuuint64_t)gc, (cuuint64_t)rows, (cuuint64_t)(d / gc)};
-    cuuint64_t gstr[2] = {(cuuint64_t)ldx * elem, 128};
-    cuuint32_t box[3] = {(cuuint32_t)gc, (cuuint32_t)bk, (cuuint32_t)elem /* groups per 128-column block */};
-    cuuint32_t estr[3] = {1, 1, 1};
-    const CUtensorMapSwizzle swz = elem == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
-    CUresult r = g_encode2(&tm_x, dt, 3, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    VLM_REQUIRE(r == CUDA_SUCCESS, VLM_ERR_DRIVER, "cuTensorMapEncodeTiled(X, 3-D) failed: CUresult %d", (int)r);
-  }
-  {
-    cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)d};
-    cuuint64_t gstr[1] = {(cuuint64_t)ldg * 4};
-    cuuint32_t box[2] = {32, 128};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode2(&tm_g, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g, gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    VLM_REQUIRE(r == CUDA_SUCCESS, VLM_ERR_DRIVER, "cuTensorMapEncodeTiled(G) failed: CUresult %d", (int)r);
-  }
+  if (int rc = encode_maps(x, dtype, rows, d, ldx, g, ldg, &tm_x, &tm_g)) return rc;
   if (dtype == VLM_F32) return launch_kernel2<4, 2>(dev, sched, tm_x, tm_g, d, stream);
   if (dtype == VLM_BF16) return launch_kernel2<2, 1>(dev, sched, tm_x, tm_g, d, stream);
   return launch_kernel2<2, 0>(dev, sched, tm_x, tm_g, d, stream);
+}
+
+
+int syrk_tc2_batch_launch(const vlm_syrk_problem* probs, int n, int dtype, cudaStream_t stream) {
+  const int elem = (dtype == VLM_F32) ? 4 : 2;
+  const int bk = 128 / elem;
+  int dev = 0, nsm = 0;
+  VLM_CUDA(cudaGetDevice(&dev));
+  if (int rc = device_sm_count(&nsm)) return rc;
+  if (int rc = ensure_encode()) return rc;
+  const int C = nsm / 2;
+  std::vector<CUtensorMap> maps(2 * (size_t)n);
+  std::vector<std::vector<BatchSeg>> per(C);
+  std::vector<int64_t> load(C, 0);
+  std::vector<PairSeg> segs;
+  std::vector<int> off;
+  for (int p = 0; p < n; ++p) {
+    const vlm_syrk_problem& q = probs[p];
+    if (int rc = check_alignment(q.x, elem, q.rows, q.ldx, q.g, q.ldg)) return rc;
+    if (int rc = encode_maps(q.x, dtype, q.rows, q.d, q.ldx, q.g, q.ldg, &maps[2 * p], &maps[2 * p + 1])) return rc;
+    build_pair_schedule((q.rows + bk - 1) / bk, q.d, C, &segs, &off);
+    // this problem's per-cluster shares go to the least loaded clusters, heaviest share first
+    std::vector<std::pair<int64_t, int>> shares;
+    for (int c = 0; c + 1 < (int)off.size(); ++c) {
+      int64_t cost = 0;
+      for (int s = off[c]; s < off[c + 1]; ++s) cost += segs[s].k1 - segs[s].k0;
+      shares.push_back({cost, c});
+    }
+    std::sort(shares.begin(), shares.end(), [](auto& a, auto& b) { return a.first > b.first || (a.first == b.first && a.second < b.second); });
+    std::vector<int> order(C);
+    for (int c = 0; c < C; ++c) order[c] = c;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return load[a] < load[b]; });
+    for (size_t i = 0; i < shares.size(); ++i) {
+      const int dst = order[i % C], c = shares[i].second;
+      for (int s = off[c]; s < off[c + 1]; ++s)
+        per[dst].push_back({segs[s].sa, segs[s].sb, segs[s].k0, segs[s].k1, p, q.d});
+      load[dst] += shares[i].first;
+    }
+  }
+  int ncl = C;
+  while (ncl > 0 && per[ncl - 1].empty()) --ncl;  // (clusters are filled least-loaded first, so gaps are rare)
+  std::vector<BatchSeg> flat;
+  std::vector<int> foff(1, 0);
+  for (int c = 0; c < ncl; ++c) {
+    flat.insert(flat.end(), per[c].begin(), per[c].end());
+    foff.push_back((int)flat.size());
+  }
+  if (flat.empty()) return 0;
+  const size_t maps_bytes = maps.size() * sizeof(CUtensorMap);
+  const size_t off_bytes = ((foff.size() * sizeof(int)) + 127) / 128 * 128;
+  const size_t seg_bytes = flat.size() * sizeof(BatchSeg);
+  const size_t total = maps_bytes + off_bytes + seg_bytes;
+  std::vector<uint8_t> host(total);
+  memcpy(host.data(), maps.data(), maps_bytes);
+  memcpy(host.data() + maps_bytes, foff.data(), foff.size() * sizeof(int));
+  memcpy(host.data() + maps_bytes + off_bytes, flat.data(), seg_bytes);
+  uint8_t* dptr = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_mu2);
+    Scratch& sc = g_scratch[{dev, stream}];
+    const int i = sc.next;
+    sc.next = (sc.next + 1) % 4;
+    if (sc.cap[i] < total) {
+      if (sc.ptr[i]) VLM_CUDA(cudaFree(sc.ptr[i]));  // synchronises: nothing in flight can still read it
+      sc.cap[i] = std::max<size_t>(total * 2, 1 << 18);
+      VLM_CUDA(cudaMalloc(&sc.ptr[i], sc.cap[i]));
+    }
+    dptr = static_cast<uint8_t*>(sc.ptr[i]);
+  }
+  // pageable source: staged before the call returns; ordered on `stream` before the kernel below
+  VLM_CUDA(cudaMemcpyAsync(dptr, host.data(), total, cudaMemcpyHostToDevice, stream));
+  auto launch = [&](auto kernel) -> int {
+    VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    kernel<<<2 * ncl, kThreads, kSmemBytes, stream>>>(maps[0], maps[1], reinterpret_cast<const CUtensorMap*>(dptr),
+                                                        dptr + maps_bytes + off_bytes,
+                                                        reinterpret_cast<const int*>(dptr + maps_bytes), 0);
+    VLM_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+  };
+  if (dtype == VLM_F32) return launch(syrk_tc2_kernel<4, 2, true>);
+  if (dtype == VLM_BF16) return launch(syrk_tc2_kernel<2, 1, true>);
+  return launch(syrk_tc2_kernel<2, 0, true>);
 }
 
 }  // namespace vlm

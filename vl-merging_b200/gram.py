@@ -83,7 +83,14 @@ class GramCache:
     at their first call get individual buffers.
     """
 
-    def __init__(self, device=None, use_simt=False):
+    def __init__(self, device=None, use_simt=False, defer_rows=0, max_pending=256):
+        """defer_rows > 0: an activation with at most that many rows is not launched on its own (a Gram of a
+        40-token text batch is launch-bound: ~7 us of fixed cost for ~2 us of tensor-core work); the hook keeps
+        a REFERENCE to it (no copy) and flush() issues everything pending as one grouped launch
+        (vlm_syrk_accum_batch).  register() then also flushes after every forward of the registered model.
+        Only safe when nothing modifies a hooked activation in place after the hooked module ran — true for the
+        VLMo blocks (LayerNorm / attention / GELU outputs are fresh tensors); the default 0 keeps the
+        reference's immediate semantics."""
         self.device = torch.device(device if device is not None else "cuda")
         if self.device.type != "cuda":
             raise RuntimeError("GramCache needs a CUDA device: the Gram hot path has no CPU fallback")
@@ -97,6 +104,8 @@ class GramCache:
         self.rows = defaultdict(int)
         self._handles = []
         self._finalized = True
+        self.defer_rows, self.max_pending = int(defer_rows), int(max_pending)
+        self._pending = []     # (dtype code, x2 (kept alive), g)
 
     # ---- the hook -------------------------------------------------------------------------------
     def hook_gram_input(self, module, input, output):
@@ -127,11 +136,30 @@ class GramCache:
             g = self.buffers[name] = torch.zeros(d, d, dtype=torch.float32, device=self.device)
         elif g.shape[0] != d:
             raise RuntimeError(f"{name}: activation width changed from {g.shape[0]} to {d}")
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        _lib.check(fn(x2.data_ptr(), _DTYPES[x2.dtype], x2.shape[0], d, ldx, g.data_ptr(), g.stride(0), stream))
         self.calls[name] += 1
         self.rows[name] += x2.shape[0]
         self._finalized = False
+        if 0 < x2.shape[0] <= self.defer_rows and fn is not self._lib.vlm_syrk_accum_simt:
+            self._pending.append((_DTYPES[x2.dtype], x2, g, ldx))
+            if len(self._pending) >= self.max_pending:
+                self.flush()
+            return
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(fn(x2.data_ptr(), _DTYPES[x2.dtype], x2.shape[0], d, ldx, g.data_ptr(), g.stride(0), stream))
+
+    def flush(self):
+        """Issue every deferred activation: one grouped launch per dtype on the current stream."""
+        if not self._pending:
+            return
+        pending, self._pending = self._pending, []
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        for code in sorted({p[0] for p in pending}):
+            group = [p for p in pending if p[0] == code]
+            probs = (_lib.SyrkProblem * len(group))()
+            for q, (_, x2, g, ldx) in zip(probs, group):
+                q.x, q.rows, q.ldx, q.g, q.ldg, q.d = x2.data_ptr(), x2.shape[0], ldx, g.data_ptr(), g.stride(0), x2.shape[1]
+            _lib.check(self._lib.vlm_syrk_accum_batch(probs, len(group), code, stream))
+        # `pending` (and with it the activations) is released here: the launches are already ordered on the stream
 
     # ---- registration ---------------------------------------------------------------------------
     def register(self, model, use_moe=True, all_keys=None):
@@ -144,6 +172,8 @@ class GramCache:
             self._handles.append(module.register_forward_hook(self.hook_gram_input))
             picked.append((name, _in_features(module)))
         self._allocate_arena([(n, d) for n, d in picked if d is not None and n not in self.buffers])
+        if self.defer_rows > 0:
+            self._handles.append(model.register_forward_hook(lambda m, i, o: self.flush()))
         return [n for n, _ in picked]
 
     def _allocate_arena(self, named_dims):
@@ -158,6 +188,7 @@ class GramCache:
         self._arenas.append(arena)
 
     def remove_hooks(self):
+        self.flush()
         for h in self._handles:
             h.remove()
         self._handles = []
@@ -170,10 +201,12 @@ class GramCache:
     def all_reduce(self, group=None):
         """Data-parallel calibration: sum the per-rank Gram buffers (NCCL all-reduce over NVLink).
         The reference has no such step (every DDP rank writes its own file)."""
+        self.flush()
         reduce_gram_buffers(self.buffers, self._arenas, self.calls, self.rows, group)
 
     def finalize(self):
         """Mirror the upper triangles into the lower ones (after the last accumulate / all_reduce)."""
+        self.flush()
         if self._finalized:
             return
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -210,6 +243,7 @@ class GramCache:
         torch.save(self.state_dict(), path)
 
     def reset(self):
+        self._pending = []
         for g in self.buffers.values():
             g.zero_()
         self.calls.clear()
