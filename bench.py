@@ -169,10 +169,31 @@ def run_ours(args):
             with torch.autocast("cuda", dtype=amp):
                 return model(batch)
 
-    def step_e2e(hb):
-        batch = {"image": [hb["image"][0].to(dev, non_blocking=True)],
-                 **{k: hb[k].to(dev, non_blocking=True) for k in ("text_ids", "text_masks", "text_labels")}}
-        return step(batch).float().cpu()   # D2H of the step's result; synchronises
+    copy_stream = torch.cuda.Stream(device=dev)
+    inflight = {}
+
+    def h2d_async(i, hb):
+        """Host -> device copy of step i's batch on a side stream (what a pin_memory DataLoader + prefetch does)."""
+        with torch.cuda.stream(copy_stream):
+            batch = {"image": [hb["image"][0].to(dev, non_blocking=True)],
+                     **{k: hb[k].to(dev, non_blocking=True) for k in ("text_ids", "text_masks", "text_labels")}}
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        inflight[i] = (batch, ev)
+
+    def step_e2e(i, nsteps):
+        """Step i end to end: its batch comes from pinned host memory (copy overlapped with step i-1's compute),
+        its logits go back to the host (synchronising)."""
+        if i not in inflight:
+            h2d_async(i, host_batches[i % 2])
+        batch, ev = inflight.pop(i)
+        torch.cuda.current_stream(dev).wait_event(ev)
+        if i + 1 < nsteps:
+            h2d_async(i + 1, host_batches[(i + 1) % 2])
+        out = step(batch)
+        for t in [batch["image"][0], batch["text_ids"], batch["text_masks"], batch["text_labels"]]:
+            t.record_stream(torch.cuda.current_stream(dev))
+        return out.float().cpu()   # D2H of the step's result; synchronises
 
     def barrier():
         if world > 1:
@@ -269,8 +290,8 @@ def run_ours(args):
     # ---- end to end: host buffers in, logits out, every step --------------------------------------
     cache.reset()
     for i in range(2):
-        step_e2e(host_batches[i % 2])
-    ms_e2e, _, _, _ = timed(lambda i: step_e2e(host_batches[i % 2]), args.steps, with_allreduce=True)
+        step_e2e(i, 2)
+    ms_e2e, _, _, _ = timed(lambda i: step_e2e(i, args.steps), args.steps, with_allreduce=True)
     h2d = sum(host_batches[0][k].numel() * host_batches[0][k].element_size() for k in ("text_ids", "text_masks", "text_labels"))
     h2d += host_batches[0]["image"][0].numel() * 4
     e2e = {"value": round(world * B * args.steps / (ms_e2e * 1e-3), 2), "unit": "samples/s",

@@ -83,14 +83,15 @@ class GramCache:
     at their first call get individual buffers.
     """
 
-    def __init__(self, device=None, use_simt=False, defer_rows=0, max_pending=256):
+    def __init__(self, device=None, use_simt=False, defer_rows=0, max_pending=256, max_pending_bytes=16 << 30):
         """defer_rows > 0: an activation with at most that many rows is not launched on its own (a Gram of a
         40-token text batch is launch-bound: ~7 us of fixed cost for ~2 us of tensor-core work); the hook keeps
         a REFERENCE to it (no copy) and flush() issues everything pending as one grouped launch
         (vlm_syrk_accum_batch).  register() then also flushes after every forward of the registered model.
         Only safe when nothing modifies a hooked activation in place after the hooked module ran — true for the
         VLMo blocks (LayerNorm / attention / GELU outputs are fresh tensors); the default 0 keeps the
-        reference's immediate semantics."""
+        reference's immediate semantics.  Deferred activations stay allocated until the flush; a flush is forced
+        after max_pending activations or max_pending_bytes of them."""
         self.device = torch.device(device if device is not None else "cuda")
         if self.device.type != "cuda":
             raise RuntimeError("GramCache needs a CUDA device: the Gram hot path has no CPU fallback")
@@ -104,8 +105,9 @@ class GramCache:
         self.rows = defaultdict(int)
         self._handles = []
         self._finalized = True
-        self.defer_rows, self.max_pending = int(defer_rows), int(max_pending)
-        self._pending = []     # (dtype code, x2 (kept alive), g)
+        self.defer_rows, self.max_pending, self.max_pending_bytes = int(defer_rows), int(max_pending), int(max_pending_bytes)
+        self._pending = []     # (dtype code, x2 (kept alive), g, ldx)
+        self._pending_bytes = 0
 
     # ---- the hook -------------------------------------------------------------------------------
     def hook_gram_input(self, module, input, output):
@@ -141,7 +143,8 @@ class GramCache:
         self._finalized = False
         if 0 < x2.shape[0] <= self.defer_rows and fn is not self._lib.vlm_syrk_accum_simt:
             self._pending.append((_DTYPES[x2.dtype], x2, g, ldx))
-            if len(self._pending) >= self.max_pending:
+            self._pending_bytes += x2.shape[0] * ldx * elem
+            if len(self._pending) >= self.max_pending or self._pending_bytes >= self.max_pending_bytes:
                 self.flush()
             return
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -151,7 +154,7 @@ class GramCache:
         """Issue every deferred activation: one grouped launch per dtype on the current stream."""
         if not self._pending:
             return
-        pending, self._pending = self._pending, []
+        pending, self._pending, self._pending_bytes = self._pending, [], 0
         stream = torch.cuda.current_stream(self.device).cuda_stream
         for code in sorted({p[0] for p in pending}):
             group = [p for p in pending if p[0] == code]
@@ -243,7 +246,7 @@ class GramCache:
         torch.save(self.state_dict(), path)
 
     def reset(self):
-        self._pending = []
+        self._pending, self._pending_bytes = [], 0
         for g in self.buffers.values():
             g.zero_()
         self.calls.clear()
