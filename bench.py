@@ -132,7 +132,7 @@ def run_ours(args):
 
         def accumulate(self, name, x):
             rows = x.numel() // x.shape[-1]
-            if not self.timing or 0 < rows <= self.defer_rows:
+            if not self.timing or 0 < x.numel() * x.element_size() <= self.defer_bytes:
                 return super().accumulate(name, x)   # deferred activations are timed in flush()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
@@ -149,9 +149,9 @@ def run_ours(args):
             a.record()
             super().flush()
             b.record()
-            self.events.append((a, b, flops, f"grouped launch of {n} small Grams (rows <= {self.defer_rows})", n))
+            self.events.append((a, b, flops, "grouped launches (text Grams + 768-wide image Grams)", n))
 
-    cache = TimedCache(dev, defer_rows=args.defer_rows)
+    cache = TimedCache(dev, defer_bytes=args.defer_mb << 20, max_pending_bytes=args.defer_cap_mb << 20)
     cache.register(model, use_moe=True)
     B = args.batch
     host_batches = [vlm.synthetic_batch(B, cfg, seed=1234 + rank * 16 + i) for i in range(2)]
@@ -357,8 +357,9 @@ def run_ours(args):
                                    "96 Grams (72 x 768^2 + 24 x 3072^2)" if args.model == "base" else f"RegMean Gram caching, VLMo-{args.model} all_moe",
                        "global_batch": world * B, "parallelism": f"dp{world}", "forward": f"stock torch ({args.attn} attention), " + ("fp32 with TF32 matmuls" if not sixteen else f"autocast {args.autocast}"),
                        "l2": "inputs larger than L2 (each step streams >2 GB of weights and activations)",
-                       "gram_hooks": (f"one SYRK launch per hooked image activation; text activations (rows <= {args.defer_rows}) "
-                                      "grouped into one launch per forward") if args.defer_rows > 0 else "one SYRK launch per hook call",
+                       "gram_hooks": (f"activations <= {args.defer_mb} MB are held by reference and issued as grouped launches "
+                                      f"(flush at {args.defer_cap_mb} MB pending and after every forward); larger ones launch "
+                                      "from the hook") if args.defer_mb > 0 else "one SYRK launch per hook call",
                        "allreduce_ms_in_timed_region": round(ar_ms, 3)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "merge": merge, "regmean": regmean, "irtr": irtr, "gram_parity_rel_fro": parity,
@@ -626,9 +627,10 @@ def main():
     ap.add_argument("--attn", default="reference", choices=["reference", "sdpa"],
                     help="attention of the stock-torch forward: the reference's explicit softmax, or torch SDPA")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra (informational) forward variants")
-    ap.add_argument("--defer-rows", type=int, default=8192,
-                    help="GramCache(defer_rows=...): activations with at most this many rows (the 40-token text tower) are "
-                         "grouped into one launch per forward; 0 = one launch per hook call")
+    ap.add_argument("--defer-mb", type=int, default=128,
+                    help="GramCache(defer_bytes=...): activations of at most this many MB (text tower, 768-wide image "
+                         "activations) are grouped into shared launches; 0 = one launch per hook call")
+    ap.add_argument("--defer-cap-mb", type=int, default=1024, help="flush grouped launches once this much is pending")
     ap.add_argument("--no-regmean", action="store_true")
     ap.add_argument("--irtr", action="store_true",
                     help="also run config 4: modality-arithmetic merge + IRTR forward over 5k synthetic images x 25k captions")

@@ -115,12 +115,12 @@ def test_registration_and_reference_file_format(tmp_path):
 
 
 def test_batched_launch_matches_individual_launches():
-    """vlm_syrk_accum_batch through GramCache(defer_rows=...): mixed shapes in one grid, incl. a column count that
+    """vlm_syrk_accum_batch through GramCache(defer_bytes=...): mixed shapes in one grid, incl. a column count that
     is not a whole number of 128-byte groups (issued individually) and two accumulations into the same Gram."""
     shapes = [(2560, 768), (2560, 3072), (40, 768), (333, 200), (1000, 1024), (2560, 768)]
     names = ["a", "b", "c", "odd", "e", "a"]
     xs = [_x(sh, torch.float32, 100 + i, positive=(i % 2 == 1)).cuda() for i, sh in enumerate(shapes)]
-    now, later = vlm.GramCache(), vlm.GramCache(defer_rows=4096)
+    now, later = vlm.GramCache(), vlm.GramCache(defer_bytes=64 << 20)
     for n, x in zip(names, xs):
         now.accumulate(n, x)
         later.accumulate(n, x)
@@ -138,7 +138,7 @@ def test_batched_launch_matches_individual_launches():
 def test_deferred_hooks_flush_after_each_forward():
     cfg = vlm.vlmo_config("tiny")
     model = vlm.init_synthetic_(vlm.VLMo(cfg).eval(), seed=1).cuda()
-    a, b = vlm.GramCache(), vlm.GramCache(defer_rows=100000)   # defer everything
+    a, b = vlm.GramCache(), vlm.GramCache(defer_bytes=1 << 40)   # defer everything
     a.register(model)
     b.register(model)
     with torch.no_grad():

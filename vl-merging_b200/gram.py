@@ -83,11 +83,13 @@ class GramCache:
     at their first call get individual buffers.
     """
 
-    def __init__(self, device=None, use_simt=False, defer_rows=0, max_pending=256, max_pending_bytes=16 << 30):
-        """defer_rows > 0: an activation with at most that many rows is not launched on its own (a Gram of a
-        40-token text batch is launch-bound: ~7 us of fixed cost for ~2 us of tensor-core work); the hook keeps
-        a REFERENCE to it (no copy) and flush() issues everything pending as one grouped launch
-        (vlm_syrk_accum_batch).  register() then also flushes after every forward of the registered model.
+    def __init__(self, device=None, use_simt=False, defer_bytes=0, max_pending=256, max_pending_bytes=1 << 30):
+        """defer_bytes > 0: an activation of at most that many bytes is not launched on its own (the Gram of a
+        40-token text batch is launch-bound: ~7 us of fixed cost for ~2 us of tensor-core work, and a 768-wide
+        image Gram exposes its prologue and final epilogue); the hook keeps a REFERENCE to it (no copy) and
+        flush() issues everything pending as one grouped launch (vlm_syrk_accum_batch), in which one problem's
+        epilogue overlaps the next one's mainloop.  register() then also flushes after every forward of the
+        registered model.
         Only safe when nothing modifies a hooked activation in place after the hooked module ran — true for the
         VLMo blocks (LayerNorm / attention / GELU outputs are fresh tensors); the default 0 keeps the
         reference's immediate semantics.  Deferred activations stay allocated until the flush; a flush is forced
@@ -105,7 +107,7 @@ class GramCache:
         self.rows = defaultdict(int)
         self._handles = []
         self._finalized = True
-        self.defer_rows, self.max_pending, self.max_pending_bytes = int(defer_rows), int(max_pending), int(max_pending_bytes)
+        self.defer_bytes, self.max_pending, self.max_pending_bytes = int(defer_bytes), int(max_pending), int(max_pending_bytes)
         self._pending = []     # (dtype code, x2 (kept alive), g, ldx)
         self._pending_bytes = 0
 
@@ -141,7 +143,7 @@ class GramCache:
         self.calls[name] += 1
         self.rows[name] += x2.shape[0]
         self._finalized = False
-        if 0 < x2.shape[0] <= self.defer_rows and fn is not self._lib.vlm_syrk_accum_simt:
+        if 0 < x2.shape[0] * ldx * elem <= self.defer_bytes and fn is not self._lib.vlm_syrk_accum_simt:
             self._pending.append((_DTYPES[x2.dtype], x2, g, ldx))
             self._pending_bytes += x2.shape[0] * ldx * elem
             if len(self._pending) >= self.max_pending or self._pending_bytes >= self.max_pending_bytes:
@@ -175,7 +177,7 @@ class GramCache:
             self._handles.append(module.register_forward_hook(self.hook_gram_input))
             picked.append((name, _in_features(module)))
         self._allocate_arena([(n, d) for n, d in picked if d is not None and n not in self.buffers])
-        if self.defer_rows > 0:
+        if self.defer_bytes > 0:
             self._handles.append(model.register_forward_hook(lambda m, i, o: self.flush()))
         return [n for n, _ in picked]
 
