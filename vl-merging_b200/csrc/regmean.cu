@@ -108,6 +108,100 @@ regmean_rhs_kernel(const float* __restrict__ w, int M, int K, int64_t ldw, const
     }
 }
 
+// Pipelined variant for the real layer shapes (K a multiple of 16, 16-byte aligned rows): 128x128 block tile,
+// 16 warps of 32x32, raw fp32 / fp64 tiles brought in by a 3-stage cp.async pipeline; widening to fp64 and
+// scale_G happen when a fragment is read from shared memory, so no converted copy is ever stored.
+constexpr int TM = 128, TN = 128, TK = 16, TSTAGES = 3;
+constexpr int W_PITCH = TK + 4;  // floats: fragment reads hit 32 distinct banks
+
+template <typename GT>
+struct RhsSmem {
+  static constexpr int G_PITCH = TN + (sizeof(GT) == 4 ? 8 : 4);  // conflict-free k-major fragment reads
+  float w[TSTAGES][TM][W_PITCH];
+  GT g[TSTAGES][TK][G_PITCH];
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+  const uint32_t d = smem_u32(smem_dst);
+  const int n = valid ? 16 : 0;  // src-size 0: zero-fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(n) : "memory");
+}
+
+template <typename GT>
+__global__ void __launch_bounds__(512, 1)
+regmean_rhs_pipelined_kernel(const float* __restrict__ w, int M, int K, int64_t ldw, const GT* __restrict__ g,
+                             int64_t ldg, double alpha, double oma, double* __restrict__ acc, int64_t ldacc,
+                             int accumulate) {
+  extern __shared__ __align__(16) uint8_t rhs_smem_raw[];
+  RhsSmem<GT>& sm = *reinterpret_cast<RhsSmem<GT>*>(rhs_smem_raw);
+  constexpr int GV = 16 / sizeof(GT);  // G elements per 16-byte chunk
+  const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;  // x walks W rows: co-running blocks share G strips
+  const int N = K;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp >> 2) * 32, wn = (warp & 3) * 32;
+  double c[4][4][2] = {};
+
+  auto load_stage = [&](int slot, int kt) {
+    const int k0 = kt * TK;
+    {  // W tile: 128 rows x 16 floats = 512 chunks, one per thread
+      const int r = tid >> 2, ch = tid & 3;
+      const bool ok = (m0 + r) < M && k0 < K;
+      cp_async16(&sm.w[slot][r][ch * 4], w + (int64_t)(ok ? m0 + r : 0) * ldw + (ok ? k0 : 0) + ch * 4, ok);
+    }
+    constexpr int chunks_per_row = TN / GV;
+    for (int e = tid; e < TK * chunks_per_row; e += 512) {  // G tile: 16 rows x 128 columns
+      const int kk = e / chunks_per_row, ch = e % chunks_per_row;
+      const bool ok = k0 < K && (n0 + ch * GV) < N;
+      cp_async16(&sm.g[slot][kk][ch * GV], g + (int64_t)(ok ? k0 + kk : 0) * ldg + (ok ? n0 + ch * GV : 0), ok);
+    }
+  };
+
+  const int nk = K / TK;
+  for (int s = 0; s < TSTAGES - 1; ++s) {
+    if (s < nk) load_stage(s, s);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(TSTAGES - 2) : "memory");
+    __syncthreads();
+    if (kt + TSTAGES - 1 < nk) load_stage((kt + TSTAGES - 1) % TSTAGES, kt + TSTAGES - 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const int slot = kt % TSTAGES;
+#pragma unroll
+    for (int ks = 0; ks < TK; ks += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = (double)sm.w[slot][wm + i * 8 + (lane >> 2)][ks + (lane & 3)];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kk = ks + (lane & 3), nn = wn + j * 8 + (lane >> 2);
+        b[j] = scaled_g((double)sm.g[slot][kk][nn], kt * TK + kk == n0 + nn, alpha, oma);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma(c[i][j][0], c[i][j][1], a[i], b[j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = m0 + wm + i * 8 + (lane >> 2);
+      const int cc = n0 + wn + j * 8 + (lane & 3) * 2;
+      if (r < M && cc < N) {  // N is even here, so the pair is either fully inside or fully outside
+        double2* o = reinterpret_cast<double2*>(acc + (int64_t)r * ldacc + cc);
+        double2 v = make_double2(c[i][j][0], c[i][j][1]);
+        if (accumulate) {
+          const double2 old = *o;
+          v.x = __dadd_rn(old.x, v.x);
+          v.y = __dadd_rn(old.y, v.y);
+        }
+        *o = v;
+      }
+    }
+}
+
 // ---- cuSOLVER through dlopen (off the hot path; keeps libvlmerge loadable without it) ----------
 typedef void* cusolverDnHandle_t;
 typedef int cusolverStatus_t;
@@ -174,8 +268,29 @@ extern "C" int vlm_regmean_rhs(const float* w, int out_f, int in_f, int64_t ldw,
               VLM_ERR_INVALID_ARG, "vlm_regmean_rhs: bad arguments");
   VLM_REQUIRE(g_dtype == VLM_F64 || g_dtype == VLM_F32, VLM_ERR_INVALID_ARG,
               "vlm_regmean_rhs: g_dtype must be VLM_F64 or VLM_F32");
-  dim3 grid((out_f + BM - 1) / BM, (in_f + BN - 1) / BN);
   auto s = static_cast<cudaStream_t>(stream);
+  const int gelem = g_dtype == VLM_F64 ? 8 : 4;
+  const bool pipelined = in_f % TK == 0 && (ldw % 4) == 0 && ((ldg * gelem) % 16) == 0 && (ldacc % 2) == 0 &&
+                         (reinterpret_cast<uintptr_t>(w) % 16) == 0 && (reinterpret_cast<uintptr_t>(g) % 16) == 0 &&
+                         (reinterpret_cast<uintptr_t>(acc) % 16) == 0;
+  if (pipelined) {
+    dim3 grid((out_f + TM - 1) / TM, (in_f + TN - 1) / TN);
+    if (g_dtype == VLM_F64) {
+      auto kernel = regmean_rhs_pipelined_kernel<double>;
+      VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RhsSmem<double>)));
+      kernel<<<grid, 512, sizeof(RhsSmem<double>), s>>>(w, out_f, in_f, ldw, static_cast<const double*>(g), ldg, alpha,
+                                                       1.0 - alpha, acc, ldacc, accumulate);
+    } else {
+      auto kernel = regmean_rhs_pipelined_kernel<float>;
+      VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RhsSmem<float>)));
+      kernel<<<grid, 512, sizeof(RhsSmem<float>), s>>>(w, out_f, in_f, ldw, static_cast<const float*>(g), ldg, alpha,
+                                                      1.0 - alpha, acc, ldacc, accumulate);
+    }
+    VLM_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
+  dim3 grid((out_f + BM - 1) / BM, (in_f + BN - 1) / BN);
   if (g_dtype == VLM_F64)
     regmean_rhs_kernel<double><<<grid, 128, 0, s>>>(w, out_f, in_f, ldw, static_cast<const double*>(g), ldg, alpha,
                                                     1.0 - alpha, acc, ldacc, accumulate);

@@ -251,7 +251,7 @@ static void merge_case(const char* name, int mode, int n_src, size_t n, size_t m
   // split into several segments to exercise the chunk table
   std::vector<vlm_merge_seg> segs;
   size_t off = 0;
-  const size_t parts[4] = {n / 2, n / 4, 777 < n ? 777 : 0, 0};
+  const size_t parts[4] = {n / 2, n / 4, n > 777 ? (size_t)777 : (size_t)0, 0};
   for (int p = 0; p < 4; ++p) {
     size_t len = p == 3 ? n - off : (parts[p] / 4) * 4;
     if (len == 0) continue;
@@ -394,6 +394,41 @@ int main(int argc, char** argv) {
     auto us = [](timespec a, timespec b) { return (b.tv_sec - a.tv_sec) * 1e6 + (b.tv_nsec - a.tv_nsec) * 1e-3; };
     printf("OVERHEAD vlm_syrk_accum: %.2f us/call to enqueue (host), %.2f us/call until drained (GPU-bound)\n",
            us(t0, t1) / n, us(t0, t2) / n);
+    return 0;
+  }
+  if (argc >= 5 && !strcmp(argv[1], "rhs")) {  // selftest rhs <out_f> <in_f> <iters>: kernel (c) timing, fp32 Gram in
+    const int out_f = atoi(argv[2]), in_f = atoi(argv[3]), iters = atoi(argv[4]);
+    std::vector<float> W((size_t)out_f * in_f), Gm((size_t)in_f * in_f);
+    for (auto& v : W) v = frand();
+    for (auto& v : Gm) v = frand();
+    float *dW, *dG;
+    double* dR;
+    CK(cudaMalloc(&dW, W.size() * 4));
+    CK(cudaMalloc(&dG, Gm.size() * 4));
+    CK(cudaMalloc(&dR, W.size() * 8));
+    CK(cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dG, Gm.data(), Gm.size() * 4, cudaMemcpyHostToDevice));
+    for (int i = 0; i < 2; ++i) VK(vlm_regmean_rhs(dW, out_f, in_f, in_f, dG, VLM_F32, in_f, 0.9, dR, in_f, 0, nullptr));
+    Timer t;
+    t.start();
+    for (int i = 0; i < iters; ++i) VK(vlm_regmean_rhs(dW, out_f, in_f, in_f, dG, VLM_F32, in_f, 0.9, dR, in_f, i > 0, nullptr));
+    const float ms = t.stop() / iters;
+    // spot check one row against the host
+    std::vector<double> got(in_f);
+    VK(vlm_regmean_rhs(dW, out_f, in_f, in_f, dG, VLM_F32, in_f, 0.9, dR, in_f, 0, nullptr));
+    CK(cudaMemcpy(got.data(), dR + (size_t)(out_f - 1) * in_f, in_f * 8, cudaMemcpyDeviceToHost));
+    double num = 0, den = 0;
+    for (int c = 0; c < in_f; ++c) {
+      double acc = 0;
+      for (int k = 0; k < in_f; ++k) {
+        const double g = Gm[(size_t)k * in_f + c];
+        acc += (double)W[(size_t)(out_f - 1) * in_f + k] * (k == c ? 0.9 * g + (1 - 0.9) * g : 0.9 * g);
+      }
+      num += (acc - got[c]) * (acc - got[c]);
+      den += acc * acc;
+    }
+    printf("RHS out=%d in=%d  %.3f ms  %.2f TFLOP/s fp64  row_relerr=%.2e\n", out_f, in_f, ms,
+           2.0 * out_f * in_f * (double)in_f / ms * 1e-9, sqrt(num / den));
     return 0;
   }
   if (argc >= 6 && !strcmp(argv[1], "case")) {  // selftest case <f32|bf16|f16> <rows> <d> <iters> [positive]
