@@ -396,6 +396,11 @@ int main(int argc, char** argv) {
            us(t0, t1) / n, us(t0, t2) / n);
     return 0;
   }
+  if (argc >= 2 && !strcmp(argv[1], "merge")) {  // only the VLMo-base sized merges (for ncu captures)
+    merge_case("wsum2 85M (base ufo)", VLM_MERGE_WSUM, 2, 85045248, 0, 5);
+    merge_case("seqlerp3 85M", VLM_MERGE_SEQ_LERP, 3, 85045248, 0, 5);
+    return g_fail;
+  }
   if (argc >= 5 && !strcmp(argv[1], "rhs")) {  // selftest rhs <out_f> <in_f> <iters>: kernel (c) timing, fp32 Gram in
     const int out_f = atoi(argv[2]), in_f = atoi(argv[3]), iters = atoi(argv[4]);
     std::vector<float> W((size_t)out_f * in_f), Gm((size_t)in_f * in_f);
