@@ -148,3 +148,27 @@ def test_deferred_hooks_flush_after_each_forward():
     assert list(ga) == list(gb) and len(gb) == 96
     worst = max(((ga[k] - gb[k]).norm() / ga[k].norm()).item() for k in ga)
     assert worst < 1e-6, worst
+
+
+def test_randomised_shape_sweep():
+    """Seeded sweep over ragged shapes and dtypes: whole and partial 128-column blocks, row counts around the
+    pipeline chunk (32 / 64 rows), widths that take the CTA-pair kernel (whole 128-byte groups) and widths that
+    take the first-generation kernel, pitched inputs.  Checker: the reference hook's fp64 arithmetic in torch."""
+    rng = np.random.default_rng(20261017)
+    dtypes = [torch.float32, torch.bfloat16, torch.float16]
+    for case in range(36):
+        dtype = dtypes[case % 3]
+        d = int(rng.choice([8, 32, 64, 96, 100, 128, 160, 200, 256, 264, 320, 512, 520, 768, 1000, 1024]))
+        rows = int(rng.choice([1, 7, 31, 32, 33, 63, 64, 65, 127, 500, 1023, 4097, 9000]))
+        pitch = d + int(rng.choice([0, 0, 8, 64]))
+        base = _x((rows, pitch), torch.float32, 1000 + case, positive=bool(case % 2)).cuda().to(dtype)
+        x = base[:, :d]
+        cache = vlm.GramCache()
+        cache.accumulate("g", x)
+        cache.accumulate("g", x)
+        xd = x.double()
+        ref = 2 * (xd.T @ xd)
+        got = cache.gram("g").double()
+        err = ((got - ref).norm() / ref.norm()).item()
+        assert torch.equal(got, got.T)
+        assert err < TOL[dtype], (case, dtype, rows, d, pitch, err)

@@ -137,3 +137,57 @@ def test_base_size_matches_oracle_on_sampled_tensors(base_sd):
         for m in ("v.", "l."):
             acc = acc + np.float32(0.75) * (np_sd[p.format(m=m)] - acc)   # oracle.sum_task_vectors' update
         assert np.array_equal(got[p.format(m="")].cpu().numpy(), acc), p
+
+
+def test_randomised_segment_tables_through_the_c_abi():
+    """Seeded sweep straight at vlm_merge_plan_*: random segment counts, sizes (incl. 0, 1, chunk boundaries),
+    source counts, modes and misalignments; expected values from torch with the reference's rounding order."""
+    import ctypes
+
+    from vl_merging_b200 import _lib
+
+    L = _lib.lib()
+    rng = np.random.default_rng(7)
+    for trial in range(12):
+        nseg = int(rng.integers(1, 9))
+        segs = (_lib.MergeSeg * nseg)()
+        keep, expect = [], []
+        for s in range(nseg):
+            n = int(rng.choice([0, 1, 3, 4, 5, 4095, 4096, 4097, 8192, 50001]))
+            n_src = int(rng.integers(1, 5))
+            mode = int(rng.integers(0, 3))
+            off = int(rng.choice([0, 0, 1, 2, 3]))
+            srcs = [torch.randn(n + 8, device="cuda") for _ in range(n_src)]
+            dst = torch.full((n + 8,), float("nan"), device="cuda")
+            coefs = [float(c) for c in rng.uniform(-1.5, 1.5, size=n_src)]
+            segs[s].dst = dst.data_ptr() + 4 * off
+            for j in range(n_src):
+                segs[s].src[j] = srcs[j].data_ptr() + 4 * off
+                segs[s].coef[j] = coefs[j]
+            segs[s].n, segs[s].n_src, segs[s].mode = n, n_src, mode
+            xs = [t[off: off + n] for t in srcs]
+            c32 = [torch.tensor(c, dtype=torch.float32, device="cuda") for c in coefs]
+            if mode == _lib.MERGE_WSUM:
+                acc = c32[0] * xs[0]
+                for c, x in zip(c32[1:], xs[1:]):
+                    acc = acc + c * x
+            elif mode == _lib.MERGE_SEQ_LERP:
+                acc = xs[0].clone()
+                for c, x in zip(c32[1:], xs[1:]):
+                    acc = acc + c * (x - acc)
+            else:
+                acc = xs[0].clone()
+                for x in xs[1:]:
+                    acc = acc + x
+                acc = acc / n_src
+            keep.append((srcs, dst, off, n))
+            expect.append(acc)
+        plan = ctypes.c_void_p()
+        _lib.check(L.vlm_merge_plan_create(segs, nseg, ctypes.byref(plan)))
+        _lib.check(L.vlm_merge_plan_run(plan, None))
+        torch.cuda.synchronize()
+        assert L.vlm_merge_plan_bytes(plan) == sum((segs[s].n_src + 1) * segs[s].n * 4 for s in range(nseg))
+        L.vlm_merge_plan_destroy(plan)
+        for (srcs, dst, off, n), want in zip(keep, expect):
+            assert torch.equal(dst[off: off + n], want), trial
+            assert torch.isnan(dst[:off]).all() and torch.isnan(dst[off + n:]).all()   # nothing written out of range

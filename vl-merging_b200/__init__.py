@@ -12,7 +12,7 @@ loudly if it is missing (there is no CPU fallback).
 from . import _lib, checkpoint, gram, irtr, merge, model, plan  # noqa: F401
 from ._lib import VlmError, build  # noqa: F401
 from .checkpoint import load_checkpoint, modify_checkpoint_vlmo, save_checkpoint  # noqa: F401
-from .gram import GramCache  # noqa: F401
+from .gram import GramCache, cache_gram_matrices  # noqa: F401
 from .irtr import irtr_features, irtr_recall  # noqa: F401
 from .merge import Merger, merge_weights, regmean, sum_task_vectors  # noqa: F401
 from .model import VLMo, init_synthetic_, synthetic_batch, vlmo_config  # noqa: F401

@@ -263,3 +263,30 @@ def hook_gram_input_factory(cache):
         cache.hook_gram_input(module, input, output)
 
     return hook_gram_input
+
+
+def cache_gram_matrices(model, batches, path=None, use_moe=True, autocast_dtype=None, group=None, **cache_kwargs):
+    """The calibration flow of src/cache_gram_matrices.py:236-349 as one call: register the hooks on `model`
+    (already on its GPU, eval mode), run it over `batches` (an iterable of batch dicts; under torch.distributed
+    each rank passes ITS shard), sum the ranks, optionally write the reference-format Gram file (rank 0 only —
+    the reference lets every rank overwrite the same path).  Returns the GramCache."""
+    import torch.distributed as dist
+
+    device = next(model.parameters()).device
+    cache = GramCache(device, **cache_kwargs)
+    cache.register(model, use_moe=use_moe)
+    try:
+        with torch.no_grad():
+            for batch in batches:
+                if autocast_dtype is None:
+                    model(batch)
+                else:
+                    with torch.autocast("cuda", dtype=autocast_dtype):
+                        model(batch)
+    finally:
+        cache.remove_hooks()
+    if group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        cache.all_reduce(group)
+    if path is not None and (not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0):
+        cache.save(path)
+    return cache
