@@ -179,7 +179,7 @@ def test_randomised_segment_tables_through_the_c_abi():
                 acc = xs[0].clone()
                 for x in xs[1:]:
                     acc = acc + x
-                acc = acc / n_src
+                acc = acc / torch.full_like(acc, float(n_src))   # true division (tensor / python scalar multiplies by 1/n on CUDA)
             keep.append((srcs, dst, off, n))
             expect.append(acc)
         plan = ctypes.c_void_p()
