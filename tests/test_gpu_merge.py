@@ -191,3 +191,19 @@ def test_randomised_segment_tables_through_the_c_abi():
         for (srcs, dst, off, n), want in zip(keep, expect):
             assert torch.equal(dst[off: off + n], want), trial
             assert torch.isnan(dst[:off]).all() and torch.isnan(dst[off + n:]).all()   # nothing written out of range
+
+
+def test_base_size_host_path_is_pipelined_and_bit_identical(base_sd):
+    """CPU checkpoint in, CPU tensors out (the reference's calling convention) at the VLMo-base size: the
+    executor overlaps H2D / kernel / D2H over groups of targets; every merged tensor must equal the
+    device-resident result bit for bit."""
+    host_sd = {k: v.cpu() for k, v in base_sd.items()}
+    stats = {}
+    got = vlm.merge_weights(host_sd, BASE_CFG, stats=stats)
+    want = vlm.merge_weights(base_sd, BASE_CFG)
+    assert stats.get("pipelined_groups", 0) >= 2
+    assert stats["h2d_bytes"] == 2 * 12 * 7_087_104 * 4 and stats["d2h_bytes"] >= 12 * 7_087_104 * 4
+    assert list(got.keys()) == list(want.keys())
+    for k, w in want.items():
+        if "transformer.blocks." in k and "gamma" not in k:
+            assert got[k].device.type == "cpu" and torch.equal(got[k], w.cpu()), k

@@ -123,24 +123,18 @@ def _run_elementwise(ops, lookup, shapes, device, out_device, group=None, stats=
                 staged.append((i, j, in_total, t))
                 in_total += _round_up(t.numel())
     arena_in = torch.empty(max(in_total, 1), dtype=torch.float32, device=device)
-    h2d = 0
-    for _, _, off, t in staged:
-        src = t.detach().reshape(-1)
-        if src.dtype != torch.float32:
-            src = src.float()
-        arena_in[off: off + src.numel()].copy_(src, non_blocking=True)
-        h2d += src.numel() * 4 if not t.is_cuda else 0
-    staged_at = {(i, j): off for i, j, off, _ in staged}
-
     arena_out = torch.empty(max(shard_size[rank], 1), dtype=torch.float32, device=device)
-    segs = (_lib.MergeSeg * max(len(mine), 1))()
-    keep = []
-    for s, i in enumerate(mine):
+    staged_at = {(i, j): off for i, j, off, _ in staged}
+    staged_by_op = {}
+    for item in staged:
+        staged_by_op.setdefault(item[0], []).append(item)
+
+    def make_seg(i):
         op = ops[i]
         n_src = len(op.srcs) + (1 if op.central else 0)
         if n_src > _lib.MERGE_MAX_SRC:
             raise RuntimeError(f"{op.dst}: {n_src} sources exceed VLM_MERGE_MAX_SRC")
-        seg = segs[s]
+        seg = _lib.MergeSeg()
         seg.dst = arena_out.data_ptr() + out_off[i] * 4
         for j in range(n_src):
             if (i, j) in staged_at:
@@ -149,27 +143,70 @@ def _run_elementwise(ops, lookup, shapes, device, out_device, group=None, stats=
                 t = lookup(op, j)
                 keep.append(t)
                 seg.src[j] = t.data_ptr()
-        coefs = ([0.0] if op.central else []) + list(op.coefs)
-        for j, c in enumerate(coefs):
+        for j, c in enumerate(([0.0] if op.central else []) + list(op.coefs)):
             seg.coef[j] = c
-        seg.n = numel[op.dst]
-        seg.n_src = n_src
-        seg.mode = op.mode
-    stream = torch.cuda.current_stream(device).cuda_stream
-    if mine:
-        plan = ctypes.c_void_p()
-        _lib.check(lib.vlm_merge_plan_create(segs, len(mine), ctypes.byref(plan)))
-        try:
-            _lib.check(lib.vlm_merge_plan_run(plan, stream))
+        seg.n, seg.n_src, seg.mode = numel[op.dst], n_src, op.mode
+        return seg
+
+    keep = []
+    cur = torch.cuda.current_stream(device)
+    # Host checkpoints in, host tensors out: cut the targets into a few groups and overlap the H2D of group
+    # g+1 with the kernel + D2H of group g (PCIe is full duplex; the kernel itself is ~0.2 ms).
+    pipelined = world == 1 and out_device.type == "cpu" and in_total * 4 >= (128 << 20) and len(mine) >= 8
+    ngroups = min(8, len(mine)) if pipelined else 1
+    bounds = [len(mine) * g // ngroups for g in range(ngroups + 1)]
+    h2d_stream = torch.cuda.Stream(device) if pipelined else cur
+    d2h_stream = torch.cuda.Stream(device) if pipelined else cur
+    host = torch.empty(max(shard_size[rank], 1), dtype=torch.float32, pin_memory=True) if pipelined else None
+    if pipelined:
+        h2d_stream.wait_stream(cur)
+        d2h_stream.wait_stream(cur)
+    h2d = 0
+    plans = []
+    try:
+        for g in range(ngroups):
+            idx = mine[bounds[g]: bounds[g + 1]]
+            if not idx:
+                continue
+            with torch.cuda.stream(h2d_stream):
+                for i in idx:
+                    for _, _, off, t in staged_by_op.get(i, ()):
+                        src = t.detach().reshape(-1)
+                        if src.dtype != torch.float32:
+                            src = src.float()
+                        arena_in[off: off + src.numel()].copy_(src, non_blocking=True)
+                        h2d += src.numel() * 4 if not t.is_cuda else 0
+            segs = (_lib.MergeSeg * len(idx))(*[make_seg(i) for i in idx])
+            plan = ctypes.c_void_p()
+            _lib.check(lib.vlm_merge_plan_create(segs, len(idx), ctypes.byref(plan)))
+            plans.append(plan)
+            if pipelined:
+                cur.wait_stream(h2d_stream)
+            _lib.check(lib.vlm_merge_plan_run(plan, cur.cuda_stream))
             if stats is not None:
                 stats["merge_bytes"] = stats.get("merge_bytes", 0) + int(lib.vlm_merge_plan_bytes(plan))
-        finally:
-            torch.cuda.current_stream(device).synchronize()
+            if pipelined:
+                lo = out_off[idx[0]]
+                hi = out_off[idx[-1]] + _round_up(numel[ops[idx[-1]].dst])
+                d2h_stream.wait_stream(cur)
+                with torch.cuda.stream(d2h_stream):
+                    host[lo:hi].copy_(arena_out[lo:hi], non_blocking=True)
+    finally:
+        cur.synchronize()
+        if pipelined:
+            h2d_stream.synchronize()
+            d2h_stream.synchronize()
+        for plan in plans:
             lib.vlm_merge_plan_destroy(plan)
 
     # all-gather of the merged shards (the path's one exchange step)
     full = layout.gather(arena_out, rank, group)
-    if out_device.type == "cpu":
+    if pipelined:
+        full = host
+        if stats is not None:
+            stats["d2h_bytes"] = stats.get("d2h_bytes", 0) + full.numel() * 4
+            stats["pipelined_groups"] = ngroups
+    elif out_device.type == "cpu":
         host = torch.empty(full.numel(), dtype=torch.float32, pin_memory=True)
         host.copy_(full, non_blocking=True)
         torch.cuda.current_stream(device).synchronize()
