@@ -51,7 +51,7 @@ uint64_t    vlm_launch_count(void);
  *     middle_representations[name] += gram.cpu()
  * G[r][c] += sum_k X[k][r] * X[k][c]  for every c >= r (upper triangle; elements below the
  * diagonal are scratch until vlm_sym_finalize).  X is the hooked activation viewed as
- * [rows, d] (f32 -> TF32 tensor cores, bf16/f16 -> f16-kind tensor cores), accumulation is fp32
+ * [rows, d] (f32 -> rounded to TF32 by TMA -> TF32 tensor cores, bf16/f16 -> f16-kind tensor cores), accumulation is fp32
  * in TMEM and fp32 in G.  Requires x 16-byte aligned and ldx*sizeof(elem) % 16 == 0, g 16-byte
  * aligned and ldg % 4 == 0; otherwise VLM_ERR_ALIGNMENT (use vlm_syrk_accum_simt).
  * rows == 0 is a no-op. */

@@ -1,7 +1,8 @@
 """GPU parity of kernel (a) through GramCache (forward-hook API -> C ABI) against the oracle
 (oracle.hook_gram_input: the reference's fp64 X^T X).  Tolerance from BASELINE.json: 1e-3 relative
-Frobenius for fp32 activations (TF32 tensor cores, fp32 accumulate); bf16/f16 activations are exact
-on the tensor cores; what is left is the fp32 accumulation over up to 36,928 rows: 1e-4."""
+Frobenius for fp32 activations (TF32 tensor cores, fp32 accumulate).  TMA rounds fp32 to TF32 on load, so the
+error is unbiased rounding noise: <= 1e-3 on a handful of rows, ~3e-5 at calibration sizes (asserted below at
+1e-4); bf16/f16 activations are exact on the tensor cores, what is left is the fp32 accumulation: 1e-4."""
 import numpy as np
 import pytest
 import torch
@@ -92,7 +93,7 @@ def test_full_size_properties(dtype, d):
     idx = torch.arange(0, d, max(1, d // 256), device="cuda")[:256]
     ref_rows = xd[:, idx].T @ xd
     err = (g.double()[idx] - ref_rows).norm() / ref_rows.norm()
-    assert err.item() < TOL[dtype]
+    assert err.item() < 1e-4      # 10x inside the BASELINE tolerance at calibration sizes, all dtypes
 
 
 def test_registration_and_reference_file_format(tmp_path):
