@@ -232,10 +232,10 @@ def run_ours(args):
         return None
 
     # ---- warm-up, then the timed region (device-resident inputs) --------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # started early: nvidia-smi takes ~0.3 s to come up
     for i in range(max(args.warmup, 3)):
         step(dev_batches[i % 2])
     cache.reset()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = vlm._lib.launch_count()
     cache.timing, cache.events = True, []
     ms, t0, t1, ar_ms = timed(lambda i: step(dev_batches[i % 2]), args.steps, with_allreduce=True)
