@@ -533,21 +533,36 @@ int syrk_tc2_batch_launch(const vlm_syrk_problem* probs, int n, int dtype, cudaS
   std::vector<CUtensorMap> maps(2 * (size_t)n);
   std::vector<std::vector<BatchSeg>> per(C);
   std::vector<int64_t> load(C, 0);
-  std::vector<PairSeg> segs;
-  std::vector<int> off;
+  // per-shape schedule (segments, per-cluster offsets, shares sorted heaviest first): a batch usually repeats a
+  // handful of shapes (36 x [2560, 768] + 12 x [2560, 3072] for the text tower), so it is built once per shape
+  struct ShapeSched {
+    std::vector<PairSeg> segs;
+    std::vector<int> off;
+    std::vector<std::pair<int64_t, int>> shares;
+  };
+  std::map<std::pair<int64_t, int>, ShapeSched> by_shape;
   for (int p = 0; p < n; ++p) {
     const vlm_syrk_problem& q = probs[p];
     if (int rc = check_alignment(q.x, elem, q.rows, q.ldx, q.g, q.ldg)) return rc;
     if (int rc = encode_maps(q.x, dtype, q.rows, q.d, q.ldx, q.g, q.ldg, &maps[2 * p], &maps[2 * p + 1])) return rc;
-    build_pair_schedule((q.rows + bk - 1) / bk, q.d, C, &segs, &off);
-    // this problem's per-cluster shares go to the least loaded clusters, heaviest share first
-    std::vector<std::pair<int64_t, int>> shares;
-    for (int c = 0; c + 1 < (int)off.size(); ++c) {
-      int64_t cost = 0;
-      for (int s = off[c]; s < off[c + 1]; ++s) cost += segs[s].k1 - segs[s].k0;
-      shares.push_back({cost, c});
+    const int64_t kc = (q.rows + bk - 1) / bk;
+    auto found = by_shape.find({kc, q.d});
+    if (found == by_shape.end()) {
+      ShapeSched ss;
+      build_pair_schedule(kc, q.d, C, &ss.segs, &ss.off);
+      for (int c = 0; c + 1 < (int)ss.off.size(); ++c) {
+        int64_t cost = 0;
+        for (int s = ss.off[c]; s < ss.off[c + 1]; ++s) cost += ss.segs[s].k1 - ss.segs[s].k0;
+        ss.shares.push_back({cost, c});
+      }
+      std::sort(ss.shares.begin(), ss.shares.end(),
+                [](auto& a, auto& b) { return a.first > b.first || (a.first == b.first && a.second < b.second); });
+      found = by_shape.emplace(std::make_pair(kc, q.d), std::move(ss)).first;
     }
-    std::sort(shares.begin(), shares.end(), [](auto& a, auto& b) { return a.first > b.first || (a.first == b.first && a.second < b.second); });
+    const std::vector<PairSeg>& segs = found->second.segs;
+    const std::vector<int>& off = found->second.off;
+    const std::vector<std::pair<int64_t, int>>& shares = found->second.shares;
+    // this problem's per-cluster shares go to the least loaded clusters, heaviest share first
     std::vector<int> order(C);
     for (int c = 0; c < C; ++c) order[c] = c;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return load[a] < load[b]; });
