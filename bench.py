@@ -235,6 +235,8 @@ def run_ours(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None   # started early: nvidia-smi takes ~0.3 s to come up
     for i in range(max(args.warmup, 3)):
         step(dev_batches[i % 2])
+    if world > 1:
+        cache.all_reduce(group)   # warm-up of the collective too (NCCL connects its channels on first use)
     cache.reset()
     launches0 = vlm._lib.launch_count()
     cache.timing, cache.events = True, []
