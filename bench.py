@@ -143,7 +143,7 @@ def run_ours(args):
         def flush(self):
             if not self.timing or not self._pending:
                 return super().flush()
-            flops = sum(syrk_flops(p[1].shape[0], p[1].shape[1]) for p in self._pending)
+            flops = sum(syrk_flops(p[4], p[5]) for p in self._pending)   # (rows, d) of each pending problem
             n = len(self._pending)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()

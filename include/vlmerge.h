@@ -64,14 +64,25 @@ int vlm_syrk_accum(const void* x, int dtype, int64_t rows, int d, int64_t ldx,
  * column count is not a whole number of 128-byte groups, are issued as individual launches. */
 typedef struct {
   const void* x;
-  int64_t     rows;
+  int64_t     rows;        /* total rows (= number of row segments * seg_rows when segmented) */
   int64_t     ldx;
   float*      g;
   int64_t     ldg;
   int32_t     d;
   int32_t     reserved;
+  int64_t     seg_rows;    /* 0: rows are one contiguous run; > 0: see vlm_syrk_accum_strided */
+  int64_t     seg_stride;  /* elements between the first rows of consecutive segments */
 } vlm_syrk_problem;
 int vlm_syrk_accum_batch(const vlm_syrk_problem* probs_host, int n, int dtype, void* stream);
+
+/* Row-sliced activation: X is rows/seg_rows SEGMENTS of seg_rows rows each (row pitch ldx), segment s starting
+ * seg_stride elements after segment s-1 — the view `h[:, a:b]` of a (B, N, D) activation that the fused
+ * vision-language route feeds to the per-modality experts (src/vilt/modules/vision_transformer.py:619-637,
+ * :667-677), where the reference's `input.reshape(-1, D)` (src/cache_gram_matrices.py:250) makes a copy.
+ * Here the slice is read in place through a 4-D tensor map.  rows must be a multiple of seg_rows;
+ * seg_stride * sizeof(elem) must be a multiple of 16.  Otherwise the contract of vlm_syrk_accum. */
+int vlm_syrk_accum_strided(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows,
+                           int64_t seg_stride, float* g, int64_t ldg, void* stream);
 
 /* Same contract on CUDA cores (fp32 FMA), any alignment.  Debug oracle on the device and the
  * path for activations TMA cannot address. */

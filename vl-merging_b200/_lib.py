@@ -39,6 +39,8 @@ class SyrkProblem(ctypes.Structure):
         ("ldg", c_int64),
         ("d", c_int32),
         ("reserved", c_int32),
+        ("seg_rows", c_int64),
+        ("seg_stride", c_int64),
     ]
 
 
@@ -55,6 +57,8 @@ SIGNATURES = {
     "vlm_launch_count": (c_uint64, []),
     "vlm_syrk_accum": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_int64, c_void_p]),
     "vlm_syrk_accum_batch": (c_int, [POINTER(SyrkProblem), c_int, c_int, c_void_p]),
+    "vlm_syrk_accum_strided": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64,
+                                       c_void_p]),
     "vlm_syrk_accum_simt": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_int64, c_void_p]),
     "vlm_sym_finalize": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p]),
     "vlm_syrk_schedule_host": (c_int, [c_int64, c_int, c_int, c_int, POINTER(c_int32), c_int, POINTER(c_int32),

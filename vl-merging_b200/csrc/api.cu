@@ -87,12 +87,47 @@ extern "C" int vlm_syrk_accum(const void* x, int dtype, int64_t rows, int d, int
     return e ? atoi(e) : 2;
   }();
   if (variant == 2 && syrk_tc2_supported(dtype, d, ldx))
-    return syrk_tc2_launch(x, dtype, rows, d, ldx, g, ldg, static_cast<cudaStream_t>(stream));
+    return syrk_tc2_launch(x, dtype, rows, d, ldx, 0, 0, g, ldg, static_cast<cudaStream_t>(stream));
   return syrk_tc_launch(x, dtype, rows, d, ldx, g, ldg, static_cast<cudaStream_t>(stream));
 }
 
+namespace {
+int check_segments(const char* who, int dtype, int64_t rows, int64_t seg_rows, int64_t seg_stride) {
+  VLM_REQUIRE(seg_rows > 0 && rows % seg_rows == 0, VLM_ERR_INVALID_ARG,
+              "%s: rows (%lld) must be a multiple of seg_rows (%lld)", who, (long long)rows, (long long)seg_rows);
+  VLM_REQUIRE(seg_stride >= 0, VLM_ERR_INVALID_ARG, "%s: seg_stride < 0", who);
+  (void)dtype;
+  return 0;
+}
+bool tma_addressable(const void* x, int elem, int64_t ldx, const float* g, int64_t ldg) {
+  return (reinterpret_cast<uintptr_t>(x) & 15) == 0 && ((ldx * elem) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(g) & 15) == 0 && (ldg & 3) == 0;
+}
+}  // namespace
+
 extern "C" int vlm_syrk_accum_simt(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,
                                    void* stream);
+
+extern "C" int vlm_syrk_accum_strided(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows,
+                                      int64_t seg_stride, float* g, int64_t ldg, void* stream) {
+  if (int rc = check_syrk_args("vlm_syrk_accum_strided", x, dtype, rows, d, ldx, g, ldg)) return rc;
+  if (rows == 0) return 0;
+  if (int rc = check_segments("vlm_syrk_accum_strided", dtype, rows, seg_rows, seg_stride)) return rc;
+  if (seg_rows == rows) return vlm_syrk_accum(x, dtype, rows, d, ldx, g, ldg, stream);
+  if (int rc = require_sm100()) return rc;
+  const int elem = dtype == VLM_F32 ? 4 : 2;
+  if (tma_addressable(x, elem, ldx, g, ldg) && ((seg_stride * elem) & 15) == 0 && syrk_tc2_supported(dtype, d, ldx))
+    return syrk_tc2_launch(x, dtype, rows, d, ldx, seg_rows, seg_stride, g, ldg, static_cast<cudaStream_t>(stream));
+  // shapes the CTA-pair kernel does not take: one launch per segment through the contiguous entry points
+  for (int64_t s = 0; s < rows / seg_rows; ++s) {
+    const char* xs = static_cast<const char*>(x) + (size_t)s * seg_stride * elem;
+    const bool ok = tma_addressable(xs, elem, ldx, g, ldg);
+    if (int rc = ok ? vlm_syrk_accum(xs, dtype, seg_rows, d, ldx, g, ldg, stream)
+                    : vlm_syrk_accum_simt(xs, dtype, seg_rows, d, ldx, g, ldg, stream))
+      return rc;
+  }
+  return 0;
+}
 
 extern "C" int vlm_syrk_accum_batch(const vlm_syrk_problem* probs, int n, int dtype, void* stream) {
   VLM_REQUIRE(n >= 0 && (probs != nullptr || n == 0), VLM_ERR_INVALID_ARG, "vlm_syrk_accum_batch: bad arguments");
@@ -104,10 +139,16 @@ extern "C" int vlm_syrk_accum_batch(const vlm_syrk_problem* probs, int n, int dt
     if (int rc = check_syrk_args("vlm_syrk_accum_batch", q.x, dtype, q.rows, q.d, q.ldx, q.g, q.ldg)) return rc;
     if (q.rows == 0) continue;
     const int elem = dtype == VLM_F32 ? 4 : 2;
-    const bool tma_ok = (reinterpret_cast<uintptr_t>(q.x) & 15) == 0 && ((q.ldx * elem) & 15) == 0 &&
-                        (reinterpret_cast<uintptr_t>(q.g) & 15) == 0 && (q.ldg & 3) == 0;
+    const bool segmented = q.seg_rows > 0 && q.seg_rows < q.rows;
+    if (segmented) {
+      if (int rc = check_segments("vlm_syrk_accum_batch", dtype, q.rows, q.seg_rows, q.seg_stride)) return rc;
+    }
+    const bool tma_ok = tma_addressable(q.x, elem, q.ldx, q.g, q.ldg) && (!segmented || ((q.seg_stride * elem) & 15) == 0);
     if (tma_ok && syrk_tc2_supported(dtype, q.d, q.ldx)) {
       grouped.push_back(q);
+    } else if (segmented) {
+      if (int rc = vlm_syrk_accum_strided(q.x, dtype, q.rows, q.d, q.ldx, q.seg_rows, q.seg_stride, q.g, q.ldg, stream))
+        return rc;
     } else if (int rc = tma_ok ? vlm_syrk_accum(q.x, dtype, q.rows, q.d, q.ldx, q.g, q.ldg, stream)
                                : vlm_syrk_accum_simt(q.x, dtype, q.rows, q.d, q.ldx, q.g, q.ldg, stream)) {
       return rc;

@@ -224,6 +224,82 @@ static void syrk_case(const char* name, int dtype, int64_t rows, int d, int mode
   CK(cudaFree(g_ref));
 }
 
+// Row-sliced activation: the view h[:, off:off+seg_rows] of an (nseg, n_tok, d) tensor, read in place
+// (vlm_syrk_accum_strided, and the same problem through vlm_syrk_accum_batch) against a host fp64 Gram of the
+// slice (host_ref) or the contiguous kernel on a packed copy of the slice.
+template <typename T>
+static void syrk_strided_case(const char* name, int dtype, int nseg, int n_tok, int off, int seg_rows, int d,
+                              bool host_ref, int iters, double tol) {
+  std::vector<T> hx((size_t)nseg * n_tok * d);
+  fill_x<T>(hx, 0);
+  const int64_t rows = (int64_t)nseg * seg_rows;
+  std::vector<T> packed((size_t)rows * d);
+  for (int s = 0; s < nseg; ++s)
+    memcpy(&packed[(size_t)s * seg_rows * d], &hx[((size_t)s * n_tok + off) * d], (size_t)seg_rows * d * sizeof(T));
+  T *dx, *dp;
+  float *g1, *g2, *g3;
+  CK(cudaMalloc(&dx, hx.size() * sizeof(T)));
+  CK(cudaMalloc(&dp, packed.size() * sizeof(T)));
+  CK(cudaMemcpy(dx, hx.data(), hx.size() * sizeof(T), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dp, packed.data(), packed.size() * sizeof(T), cudaMemcpyHostToDevice));
+  for (float** g : {&g1, &g2, &g3}) {
+    CK(cudaMalloc(g, (size_t)d * d * 4));
+    CK(cudaMemset(*g, 0, (size_t)d * d * 4));
+  }
+  const T* slice = dx + (size_t)off * d;
+  VK(vlm_syrk_accum_strided(slice, dtype, rows, d, d, seg_rows, (int64_t)n_tok * d, g1, d, nullptr));
+  vlm_syrk_problem pr[2];
+  memset(pr, 0, sizeof(pr));
+  pr[0].x = slice, pr[0].rows = rows, pr[0].ldx = d, pr[0].g = g2, pr[0].ldg = d, pr[0].d = d;
+  pr[0].seg_rows = seg_rows, pr[0].seg_stride = (int64_t)n_tok * d;
+  pr[1].x = dp, pr[1].rows = rows, pr[1].ldx = d, pr[1].g = g3, pr[1].ldg = d, pr[1].d = d;  // contiguous twin
+  VK(vlm_syrk_accum_batch(pr, 2, dtype, nullptr));
+  CK(cudaDeviceSynchronize());
+  std::vector<float> o1((size_t)d * d), o2((size_t)d * d), o3((size_t)d * d);
+  CK(cudaMemcpy(o1.data(), g1, o1.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(o2.data(), g2, o2.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(o3.data(), g3, o3.size() * 4, cudaMemcpyDeviceToHost));
+  std::vector<double> ref((size_t)d * d, 0.0);
+  if (host_ref) {
+    for (int64_t k = 0; k < rows; ++k) {
+      const T* xr = &packed[(size_t)k * d];
+      for (int r = 0; r < d; ++r) {
+        const double a = to_d(xr[r]);
+        double* o = &ref[(size_t)r * d];
+        for (int c = r; c < d; ++c) o[c] += a * to_d(xr[c]);
+      }
+    }
+  } else {
+    for (size_t i = 0; i < ref.size(); ++i) ref[i] = o3[i];  // contiguous kernel on the packed copy
+  }
+  double ma = 0;
+  int wr = -1, wc = -1;
+  const double e1 = upper_rel_err(o1, ref, d, &ma, &wr, &wc);
+  const double e2 = upper_rel_err(o2, ref, d, &ma, &wr, &wc);
+  float ms = 0, ms_packed = 0;
+  if (iters > 0) {
+    Timer t;
+    for (int i = 0; i < 3; ++i)
+      VK(vlm_syrk_accum_strided(slice, dtype, rows, d, d, seg_rows, (int64_t)n_tok * d, g1, d, nullptr));
+    t.start();
+    for (int i = 0; i < iters; ++i)
+      VK(vlm_syrk_accum_strided(slice, dtype, rows, d, d, seg_rows, (int64_t)n_tok * d, g1, d, nullptr));
+    ms = t.stop() / iters;
+    t.start();
+    for (int i = 0; i < iters; ++i) VK(vlm_syrk_accum(dp, dtype, rows, d, d, g3, d, nullptr));
+    ms_packed = t.stop() / iters;
+  }
+  const bool ok = e1 <= tol && e2 <= tol && std::isfinite(e1) && std::isfinite(e2);
+  printf("SYRK-STRIDED %-24s segs=%d x %d rows (of %d) d=%-5d relF=%.3e batch=%.3e  %.3f ms (packed copy: %.3f ms)  %s\n",
+         name, nseg, seg_rows, n_tok, d, e1, e2, ms, ms_packed, ok ? "OK" : "FAIL");
+  if (!ok) ++g_fail;
+  CK(cudaFree(dx));
+  CK(cudaFree(dp));
+  CK(cudaFree(g1));
+  CK(cudaFree(g2));
+  CK(cudaFree(g3));
+}
+
 // ---- merge ---------------------------------------------------------------------------------
 static void merge_case(const char* name, int mode, int n_src, size_t n, size_t misalign, int iters) {
   std::vector<std::vector<float>> hs(n_src, std::vector<float>(n));
@@ -471,6 +547,14 @@ int main(int argc, char** argv) {
   syrk_case<__half>("f16 d=768 positive", VLM_F16, 1000, 768, 1, true, 0, 1e-5);
   syrk_case<__nv_bfloat16>("bf16 d=200 ragged", VLM_BF16, 77, 200, 1, true, 0, 1e-5);
   syrk_case<float>("f32 d=768 positive", VLM_F32, 2560, 768, 1, true, 0, 2e-3);
+
+  // row-sliced activations of the fused vision-language route: text rows [0, 40), image rows [40, 617)
+  syrk_strided_case<float>("f32 text slice", VLM_F32, 8, 617, 0, 40, 768, true, 0, 2e-3);
+  syrk_strided_case<float>("f32 image slice", VLM_F32, 4, 617, 40, 577, 768, true, 0, 2e-3);
+  syrk_strided_case<__nv_bfloat16>("bf16 image slice", VLM_BF16, 4, 617, 40, 577, 768, true, 0, 1e-5);
+  syrk_strided_case<float>("f32 d=200 (gen-1 path)", VLM_F32, 3, 50, 7, 33, 200, true, 0, 2e-3);
+  syrk_strided_case<float>("f32 image slice x64", VLM_F32, 64, 617, 40, 577, 768, false, 20, 2e-4);
+  syrk_strided_case<float>("f32 text slice x64", VLM_F32, 64, 617, 0, 40, 768, false, 20, 2e-4);
 
   // hot shapes: SIMT kernel as the reference, timed
   syrk_case<float>("f32 text d=768", VLM_F32, 2560, 768, 0, false, 20, 2e-3);

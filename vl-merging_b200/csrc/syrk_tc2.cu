@@ -72,6 +72,23 @@ __device__ __forceinline__ void tma_load_3d_mcast(const CUtensorMap* tm, uint64_
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// 4-D variants for row-SEGMENTED activations {column in group, row in segment, column group, segment}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint64_t* bar, void* smem_dst, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_mcast(const CUtensorMap* tm, uint64_t* bar, void* smem_dst, int c0,
+                                                  int c1, int c2, int c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5, %6, %7}], [%2], %3;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 // tcgen05.commit arriving on the mbarrier at this smem offset in every CTA of `mask`
 __device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -82,8 +99,9 @@ __device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t mask) {
 
 // One unit of work of a cluster in a BATCHED launch (several independent Gram problems in one grid): as PairSeg,
 // plus which problem it belongs to (index into the tensor-map array) and that problem's column count.
+// cps = chunks per row segment of a segmented activation (0: contiguous rows, 3-D tensor map).
 struct BatchSeg {
-  int32_t sa, sb, k0, k1, pid, d;
+  int32_t sa, sb, k0, k1, pid, d, cps, pad;
 };
 __device__ __forceinline__ void tensormap_acquire(const CUtensorMap* tm) {
   asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
@@ -96,7 +114,7 @@ template <int ELEM_BYTES, int FMT, bool BATCH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_g1,
                 const CUtensorMap* __restrict__ maps, const void* __restrict__ segs_raw,
-                const int* __restrict__ seg_off, int d1) {
+                const int* __restrict__ seg_off, int d1, int cps1) {
   using G = Geo<ELEM_BYTES>;
   using Seg = typename std::conditional<BATCH, BatchSeg, PairSeg>::type;
   const Seg* __restrict__ segs = static_cast<const Seg*>(segs_raw);
@@ -108,6 +126,9 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant
   };
   auto cols_of = [&](const Seg& sg) -> int {
     if constexpr (BATCH) return sg.d; else return d1;
+  };
+  auto cps_of = [&](const Seg& sg) -> int {
+    if constexpr (BATCH) return sg.cps; else return cps1;
   };
   constexpr int kRows = G::BK;            // rows of X per pipeline stage
   constexpr int kBlk = kBlockBytes;       // bytes of one 128-column block per stage
@@ -175,13 +196,27 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant
       const int a_group = (2 * seg.sa + (int)rank) * G::GB;       // first column group of this CTA's A block
       const int b_group = (2 * seg.sb + (int)rank) * G::GB;       // ... of the B block this CTA fetches
       const uint32_t bytes = (diag ? 2u : 3u) * kBlk;             // both B blocks (+ own A block)
+      // segmented activation: chunk k = (row segment k / cps, chunk k % cps inside it); rows past the end of a
+      // segment are zero-filled by TMA (they lie outside the tensor map's row dimension)
+      const int cps = cps_of(seg);
+      int xseg = cps > 0 ? seg.k0 / cps : 0;
+      int kin = seg.k0 - xseg * cps;
       for (int k = seg.k0; k < seg.k1; ++k) {
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full[stage], bytes);
         uint8_t* sb = stage_base + stage * kStageB;
-        const int row = k * kRows;
-        tma_load_3d_mcast(tm_x, &full[stage], sb + rank * kBlk, 0, row, b_group, (uint16_t)0x3);
-        if (!diag) tma_load_3d(tm_x, &full[stage], sb + 2 * kBlk, 0, row, a_group);
+        const int row = kin * kRows;
+        if (cps > 0) {
+          tma_load_4d_mcast(tm_x, &full[stage], sb + rank * kBlk, 0, row, b_group, xseg, (uint16_t)0x3);
+          if (!diag) tma_load_4d(tm_x, &full[stage], sb + 2 * kBlk, 0, row, a_group, xseg);
+        } else {
+          tma_load_3d_mcast(tm_x, &full[stage], sb + rank * kBlk, 0, row, b_group, (uint16_t)0x3);
+          if (!diag) tma_load_3d(tm_x, &full[stage], sb + 2 * kBlk, 0, row, a_group);
+        }
+        if (++kin == cps) {
+          kin = 0;
+          ++xseg;
+        }
         if (++stage == kNStages) {
           stage = 0;
           phase ^= 1;
@@ -322,8 +357,9 @@ int ensure_encode() {
 }
 
 // X as a 3-D tensor {column in group, row, column group} (strides: row pitch, 128 bytes); G as a 2-D fp32 tensor
-int encode_maps(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg, CUtensorMap* tm_x,
-                CUtensorMap* tm_g) {
+// (seg_rows > 0: 4-D, {column in group, row in segment, column group, segment})
+int encode_maps(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
+                float* g, int64_t ldg, CUtensorMap* tm_x, CUtensorMap* tm_g) {
   const int elem = (dtype == VLM_F32) ? 4 : 2;
   const int bk = 128 / elem, gc = 128 / elem;
   {
@@ -334,14 +370,18 @@ int encode_maps(const void* x, int dtype, int64_t rows, int d, int64_t ldx, floa
     const CUtensorMapDataType dt = dtype == VLM_F32    ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
                                    : dtype == VLM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                                        : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    cuuint64_t gdim[3] = {(cuuint64_t)gc, (cuuint64_t)rows, (cuuint64_t)(d / gc)};
-    cuuint64_t gstr[2] = {(cuuint64_t)ldx * elem, 128};
-    cuuint32_t box[3] = {(cuuint32_t)gc, (cuuint32_t)bk, (cuuint32_t)elem /* groups per 128-column block */};
-    cuuint32_t estr[3] = {1, 1, 1};
+    const bool segmented = seg_rows > 0;
+    cuuint64_t gdim[4] = {(cuuint64_t)gc, (cuuint64_t)(segmented ? seg_rows : rows), (cuuint64_t)(d / gc),
+                          (cuuint64_t)(segmented ? rows / seg_rows : 1)};
+    cuuint64_t gstr[3] = {(cuuint64_t)ldx * elem, 128, (cuuint64_t)seg_stride * elem};
+    cuuint32_t box[4] = {(cuuint32_t)gc, (cuuint32_t)bk, (cuuint32_t)elem /* groups per 128-column block */, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUtensorMapSwizzle swz = elem == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
-    CUresult r = g_encode2(tm_x, dt, 3, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    VLM_REQUIRE(r == CUDA_SUCCESS, VLM_ERR_DRIVER, "cuTensorMapEncodeTiled(X, 3-D) failed: CUresult %d", (int)r);
+    CUresult r = g_encode2(tm_x, dt, segmented ? 4 : 3, const_cast<void*>(x), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VLM_REQUIRE(r == CUDA_SUCCESS, VLM_ERR_DRIVER, "cuTensorMapEncodeTiled(X, %d-D) failed: CUresult %d",
+                segmented ? 4 : 3, (int)r);
   }
   {
     cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)d};
@@ -375,14 +415,14 @@ std::map<std::pair<int, cudaStream_t>, Scratch> g_scratch;
 
 template <int ELEM_BYTES, int FMT>
 int launch_kernel2(int dev, const DeviceSchedule2& sched, const CUtensorMap& tm_x, const CUtensorMap& tm_g, int d,
-                   cudaStream_t stream) {
+                   int cps, cudaStream_t stream) {
   static std::atomic<bool> attr_done[64];
   auto kernel = syrk_tc2_kernel<ELEM_BYTES, FMT, false>;
   if (dev >= 64 || !attr_done[dev].load(std::memory_order_acquire)) {
     VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     if (dev < 64) attr_done[dev].store(true, std::memory_order_release);
   }
-  kernel<<<2 * sched.nclusters, kThreads, kSmemBytes, stream>>>(tm_x, tm_g, nullptr, sched.d_segs, sched.d_off, d);
+  kernel<<<2 * sched.nclusters, kThreads, kSmemBytes, stream>>>(tm_x, tm_g, nullptr, sched.d_segs, sched.d_off, d, cps);
   VLM_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -483,16 +523,30 @@ bool syrk_tc2_supported(int dtype, int d, int64_t ldx) {
   return d % (128 / elem) == 0 && ldx >= d;  // whole 128-byte column groups (the 3-D tensor map needs them)
 }
 
-int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,
-                    cudaStream_t stream) {
+// chunks per row segment (0 = contiguous) and in total
+static inline void seg_chunks(int64_t rows, int64_t seg_rows, int bk, int64_t* cps, int64_t* kc) {
+  if (seg_rows > 0) {
+    *cps = (seg_rows + bk - 1) / bk;
+    *kc = (rows / seg_rows) * *cps;
+  } else {
+    *cps = 0;
+    *kc = (rows + bk - 1) / bk;
+  }
+}
+
+int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
+                    float* g, int64_t ldg, cudaStream_t stream) {
   const int elem = (dtype == VLM_F32) ? 4 : 2;
   const int bk = 128 / elem;  // rows per pipeline stage = schedule chunk
   if (int rc = check_alignment(x, elem, rows, ldx, g, ldg)) return rc;
+  if (seg_rows >= rows) seg_rows = 0;  // one segment: plain rows
   int dev = 0, nsm = 0;
   VLM_CUDA(cudaGetDevice(&dev));
   if (int rc = device_sm_count(&nsm)) return rc;
   if (int rc = ensure_encode()) return rc;
-  const int64_t kc = (rows + bk - 1) / bk;
+  int64_t cps, kc;
+  seg_chunks(rows, seg_rows, bk, &cps, &kc);
+  VLM_REQUIRE(kc < (int64_t)1 << 30, VLM_ERR_INVALID_ARG, "vlm_syrk_accum: too many row chunks");
   DeviceSchedule2 sched;
   {
     std::lock_guard<std::mutex> lk(g_mu2);
@@ -515,10 +569,10 @@ int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, 
   }
 
   CUtensorMap tm_x, tm_g;
-  if (int rc = encode_maps(x, dtype, rows, d, ldx, g, ldg, &tm_x, &tm_g)) return rc;
-  if (dtype == VLM_F32) return launch_kernel2<4, 2>(dev, sched, tm_x, tm_g, d, stream);
-  if (dtype == VLM_BF16) return launch_kernel2<2, 1>(dev, sched, tm_x, tm_g, d, stream);
-  return launch_kernel2<2, 0>(dev, sched, tm_x, tm_g, d, stream);
+  if (int rc = encode_maps(x, dtype, rows, d, ldx, seg_rows, seg_stride, g, ldg, &tm_x, &tm_g)) return rc;
+  if (dtype == VLM_F32) return launch_kernel2<4, 2>(dev, sched, tm_x, tm_g, d, (int)cps, stream);
+  if (dtype == VLM_BF16) return launch_kernel2<2, 1>(dev, sched, tm_x, tm_g, d, (int)cps, stream);
+  return launch_kernel2<2, 0>(dev, sched, tm_x, tm_g, d, (int)cps, stream);
 }
 
 
@@ -544,8 +598,12 @@ int syrk_tc2_batch_launch(const vlm_syrk_problem* probs, int n, int dtype, cudaS
   for (int p = 0; p < n; ++p) {
     const vlm_syrk_problem& q = probs[p];
     if (int rc = check_alignment(q.x, elem, q.rows, q.ldx, q.g, q.ldg)) return rc;
-    if (int rc = encode_maps(q.x, dtype, q.rows, q.d, q.ldx, q.g, q.ldg, &maps[2 * p], &maps[2 * p + 1])) return rc;
-    const int64_t kc = (q.rows + bk - 1) / bk;
+    const int64_t seg_rows = (q.seg_rows > 0 && q.seg_rows < q.rows) ? q.seg_rows : 0;
+    if (int rc = encode_maps(q.x, dtype, q.rows, q.d, q.ldx, seg_rows, q.seg_stride, q.g, q.ldg, &maps[2 * p],
+                             &maps[2 * p + 1]))
+      return rc;
+    int64_t cps, kc;
+    seg_chunks(q.rows, seg_rows, bk, &cps, &kc);
     auto found = by_shape.find({kc, q.d});
     if (found == by_shape.end()) {
       ShapeSched ss;
@@ -569,7 +627,7 @@ int syrk_tc2_batch_launch(const vlm_syrk_problem* probs, int n, int dtype, cudaS
     for (size_t i = 0; i < shares.size(); ++i) {
       const int dst = order[i % C], c = shares[i].second;
       for (int s = off[c]; s < off[c + 1]; ++s)
-        per[dst].push_back({segs[s].sa, segs[s].sb, segs[s].k0, segs[s].k1, p, q.d});
+        per[dst].push_back({segs[s].sa, segs[s].sb, segs[s].k0, segs[s].k1, p, q.d, (int)cps, 0});
       load[dst] += shares[i].first;
     }
   }
@@ -609,7 +667,7 @@ int syrk_tc2_batch_launch(const vlm_syrk_problem* probs, int n, int dtype, cudaS
     VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     kernel<<<2 * ncl, kThreads, kSmemBytes, stream>>>(maps[0], maps[1], reinterpret_cast<const CUtensorMap*>(dptr),
                                                         dptr + maps_bytes + off_bytes,
-                                                        reinterpret_cast<const int*>(dptr + maps_bytes), 0);
+                                                        reinterpret_cast<const int*>(dptr + maps_bytes), 0, 0);
     VLM_CUDA(cudaGetLastError());
     count_launch();
     return 0;

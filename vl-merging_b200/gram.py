@@ -127,30 +127,51 @@ class GramCache:
         x = x.detach()
         if x.dtype not in _DTYPES:
             x = x.float()
-        x2 = x.reshape(-1, d)
-        if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) < d):
-            x2 = x2.contiguous()
-        elem = x2.element_size()
-        ldx = x2.stride(0) if x2.shape[0] > 1 else d
-        fn = self._fn
-        if (x2.data_ptr() % 16) or ((ldx * elem) % 16):
-            fn = self._lib.vlm_syrk_accum_simt  # TMA cannot address it; CUDA-core kernel, same contract
+        elem = x.element_size()
+        seg_rows = seg_stride = 0
+        try:
+            x2 = x.view(-1, d)          # the reference's input.reshape(-1, D) when it is a view
+        except RuntimeError:
+            x2 = None
+        if x2 is None and x.dim() == 3 and x.stride(2) == 1 and x.stride(1) >= d and x.shape[0] > 1 \
+                and (x.stride(0) * elem) % 16 == 0 and x.stride(0) >= 0:
+            # a row slice h[:, a:b] of a (B, N, D) activation (the fused vision-language route hands these to the
+            # per-modality experts): read in place as B row segments, where the reference's reshape copies
+            rows, ldx, seg_rows, seg_stride, keep = x.shape[0] * x.shape[1], x.stride(1), x.shape[1], x.stride(0), x
+        else:
+            if x2 is None:
+                x2 = x.reshape(-1, d)
+            if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) < d):
+                x2 = x2.contiguous()
+            rows, ldx, keep = x2.shape[0], (x2.stride(0) if x2.shape[0] > 1 else d), x2
+        ptr = keep.data_ptr()
+        simt = self._fn is self._lib.vlm_syrk_accum_simt or (ptr % 16) or ((ldx * elem) % 16)
+        if simt and seg_rows:
+            keep = x.contiguous()        # the CUDA-core kernel takes plain rows only
+            ptr, ldx, seg_rows, seg_stride = keep.data_ptr(), d, 0, 0
         g = self.buffers.get(name)
         if g is None:
             g = self.buffers[name] = torch.zeros(d, d, dtype=torch.float32, device=self.device)
         elif g.shape[0] != d:
             raise RuntimeError(f"{name}: activation width changed from {g.shape[0]} to {d}")
         self.calls[name] += 1
-        self.rows[name] += x2.shape[0]
+        self.rows[name] += rows
         self._finalized = False
-        if 0 < x2.shape[0] * ldx * elem <= self.defer_bytes and fn is not self._lib.vlm_syrk_accum_simt:
-            self._pending.append((_DTYPES[x2.dtype], x2, g, ldx))
-            self._pending_bytes += x2.shape[0] * ldx * elem
+        code = _DTYPES[keep.dtype]
+        nbytes = rows * ldx * elem
+        if 0 < nbytes <= self.defer_bytes and not simt:
+            self._pending.append((code, keep, g, ptr, rows, d, ldx, seg_rows, seg_stride))
+            self._pending_bytes += nbytes
             if len(self._pending) >= self.max_pending or self._pending_bytes >= self.max_pending_bytes:
                 self.flush()
             return
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        _lib.check(fn(x2.data_ptr(), _DTYPES[x2.dtype], x2.shape[0], d, ldx, g.data_ptr(), g.stride(0), stream))
+        if seg_rows:
+            _lib.check(self._lib.vlm_syrk_accum_strided(ptr, code, rows, d, ldx, seg_rows, seg_stride, g.data_ptr(),
+                                                        g.stride(0), stream))
+        else:
+            fn = self._lib.vlm_syrk_accum_simt if simt else self._fn
+            _lib.check(fn(ptr, code, rows, d, ldx, g.data_ptr(), g.stride(0), stream))
 
     def flush(self):
         """Issue every deferred activation: one grouped launch per dtype on the current stream."""
@@ -161,8 +182,9 @@ class GramCache:
         for code in sorted({p[0] for p in pending}):
             group = [p for p in pending if p[0] == code]
             probs = (_lib.SyrkProblem * len(group))()
-            for q, (_, x2, g, ldx) in zip(probs, group):
-                q.x, q.rows, q.ldx, q.g, q.ldg, q.d = x2.data_ptr(), x2.shape[0], ldx, g.data_ptr(), g.stride(0), x2.shape[1]
+            for q, (_, _keep, g, ptr, rows, d, ldx, seg_rows, seg_stride) in zip(probs, group):
+                q.x, q.rows, q.ldx, q.g, q.ldg, q.d = ptr, rows, ldx, g.data_ptr(), g.stride(0), d
+                q.seg_rows, q.seg_stride = seg_rows, seg_stride
             _lib.check(self._lib.vlm_syrk_accum_batch(probs, len(group), code, stream))
         # `pending` (and with it the activations) is released here: the launches are already ordered on the stream
 

@@ -11,9 +11,11 @@ mirrors the reference's module tree and parameter names, so that
 Reference it follows: src/vilt/modules/vision_transformer.py:272-363 (Mlp, Attention), :366-691
 (Block: moe_forward / separate_plain_forward for type_id 0 and 1), :952-991 (visual_embed);
 src/vilt/modules/vilt_module.py:122-186 (relative position index tables), :1226-1285
-(infer_text_ft), :1378-1464 (infer_image_ft).  Only the two fine-tuning towers used by IRTR
-calibration and evaluation are implemented (type_id 0 = image, 1 = text); the fused `vl` route,
-heads and losses are out of scope.
+(infer_text_ft), :1378-1464 (infer_image_ft), :1071-1156 (infer: the fused vision-language route,
+type_id 2, vision_transformer.py:495-523, :560-681).  The two fine-tuning towers (type_id 0 = image,
+1 = text) serve IRTR calibration and evaluation; `infer` serves Gram caching for VQA / NLVR2 style
+tasks, where the `vl` experts run and the shallow layers hand ROW SLICES of the joint sequence to the
+`l` / `v` experts.  Task heads and losses are out of scope.
 """
 import math
 
@@ -79,9 +81,11 @@ class Block(nn.Module):
     """One multiway block.  experts = ("v","l") / ("v","l","vl") gives the modality-specific (all_moe)
     layout with per-expert attention, MLP and both LayerNorms; experts = None the shared (ufo) one."""
 
-    def __init__(self, dim, num_heads, mlp_ratio, experts, attn_impl="reference"):
+    def __init__(self, dim, num_heads, mlp_ratio, experts, attn_impl="reference", joint=False, max_text_len=40):
         super().__init__()
         self.experts = experts
+        self.joint = joint                # layer >= vlffn_start_layer_index: "vl" is among this layer's tasks
+        self.max_text_len = max_text_len
         hidden = int(dim * mlp_ratio)
         ln = lambda: nn.LayerNorm(dim, eps=1e-6)  # noqa: E731
         if experts is None:
@@ -96,6 +100,8 @@ class Block(nn.Module):
         self.gamma_2 = nn.Parameter(0.1 * torch.ones(dim))
 
     def forward(self, x, mask, type_id, relative_position_bias):
+        if type_id == 2 and not self.joint:
+            return self._forward_split(x, mask, relative_position_bias)
         if self.experts is None:
             attn, norm1, mlp, norm2 = self.attn, self.norm1, self.mlp, self.norm2
         else:
@@ -103,6 +109,23 @@ class Block(nn.Module):
             attn, norm1, mlp, norm2 = self.attn[m], self.norm1[m], self.mlp[m], self.norm2[m]
         x = x + self.gamma_1 * attn(norm1(x), mask=mask, relative_position_bias=relative_position_bias)
         x = x + self.gamma_2 * mlp(norm2(x))
+        return x
+
+    def _forward_split(self, x, mask, bias):
+        """type_id 2 on a layer WITHOUT a `vl` expert: text tokens [0, L) go through the `l` expert, image tokens
+        [L, N) through the `v` expert, each attending only to its own modality (vision_transformer.py:510-516,
+        :619-637, :667-677; shared weights: :540-556, :586-598).  As in the reference the LayerNorm output is
+        concatenated first and the experts receive SLICES of it, so their forward hooks see non-contiguous
+        (B, n, D) views — which GramCache reads in place (vlm_syrk_accum_strided)."""
+        L = self.max_text_len
+        moe = self.experts is not None
+        pick = (lambda mod, m: mod[m]) if moe else (lambda mod, m: mod)
+        h = torch.cat([pick(self.norm1, "l")(x[:, :L]), pick(self.norm1, "v")(x[:, L:])], dim=1)
+        a_t = pick(self.attn, "l")(h[:, :L], mask=mask[:, :L], relative_position_bias=bias[:, :L, :L])
+        a_i = pick(self.attn, "v")(h[:, L:], mask=mask[:, L:], relative_position_bias=bias[:, L:, L:])
+        x = x + self.gamma_1 * torch.cat([a_t, a_i], dim=1)
+        h = torch.cat([pick(self.norm2, "l")(x[:, :L]), pick(self.norm2, "v")(x[:, L:])], dim=1)
+        x = x + self.gamma_2 * torch.cat([pick(self.mlp, "l")(h[:, :L]), pick(self.mlp, "v")(h[:, L:])], dim=1)
         return x
 
 
@@ -123,7 +146,8 @@ class Transformer(nn.Module):
         self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
         self.mask_token = nn.Parameter(torch.zeros(1, 1, dim))
         self.blocks = nn.ModuleList(
-            [Block(dim, cfg["num_heads"], cfg["mlp_ratio"], experts_for_layer(i), cfg.get("attn_impl", "reference"))
+            [Block(dim, cfg["num_heads"], cfg["mlp_ratio"], experts_for_layer(i), cfg.get("attn_impl", "reference"),
+                   joint=i >= cfg["vlffn_start_layer_index"], max_text_len=cfg["max_text_len"])
              for i in range(cfg["num_layers"])])
         self.norm = nn.LayerNorm(dim, eps=1e-6)
 
@@ -255,6 +279,27 @@ class VLMo(nn.Module):
         feats = self.transformer.norm(x)
         cls = self.ifm_image_proj.fc(feats[:, 0])
         return {"image_feats": feats, "cls_feats": cls / cls.norm(dim=-1, keepdim=True), "raw_cls_feats": x[:, 0]}
+
+    def infer(self, batch, image_token_type_idx=1):
+        """The fused vision-language route (vilt_module.py:1071-1156): text and image tokens in ONE sequence,
+        every block called with type_id 2 — `vl` experts on all 40 + 577 tokens where a layer has them, row
+        slices through the `l` / `v` experts below vlffn_start_layer_index."""
+        img = batch["image"][0] if isinstance(batch["image"], (list, tuple)) else batch["image"]
+        ids, text_masks = batch["text_ids"], batch["text_masks"]
+        text = self.text_embeddings(ids)
+        image, image_masks = self.transformer.visual_embed(img)
+        image_masks = image_masks.type_as(text_masks)
+        text = text + self.token_type_embeddings(torch.zeros_like(text_masks))
+        image = image + self.token_type_embeddings(torch.full_like(image_masks, image_token_type_idx))
+        x = torch.cat([text, image], dim=1)
+        masks = torch.cat([text_masks, image_masks], dim=1)
+        biases = self._rel_pos_bias(self.text_imag_relative_position_index.long())
+        for i, blk in enumerate(self.transformer.blocks):
+            x = blk(x, masks, 2, biases[i])
+        x = self.transformer.norm(x)
+        n_text = text.shape[1]
+        return {"text_feats": x[:, :n_text], "image_feats": x[:, n_text:],
+                "cls_feats": torch.tanh(self.pooler.dense(x[:, 0])), "raw_cls_feats": x[:, 0]}
 
     def forward(self, batch):
         """One IRTR calibration step (objectives.py:372-379): both towers, similarity logits."""
