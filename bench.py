@@ -338,7 +338,7 @@ def run_ours(args):
     merge = bench_merge(vlm, model, cfg, dev, group, world, rank, peaks, args)
 
     # ---- config 3: full RegMean merge from the cached Grams (kernel (c) + cuSOLVER, timed separately) ----
-    regmean = None
+    regmean = gram_file = None
     if not args.no_regmean:
         cache.reset()
         for i in range(2):  # 2 x 64 x 40 = 5120 text rows >= 3072: every summed Gram is full rank
@@ -346,6 +346,44 @@ def run_ours(args):
         if world > 1:
             cache.all_reduce(group)
         regmean = bench_regmean(vlm, model, cfg, cache, dev, group, world, args)
+        if world == 1 and not args.no_gramfile:
+            gram_file = bench_gramfile(vlm, cache, dev)
+        cache.reset()
+
+    # ---- Gram caching on the fused vision-language route (type_id 2) ----
+    fused = None
+    if args.fused:
+        def fstep(i):
+            with torch.no_grad():
+                model.infer(dev_batches[i % 2])
+            cache.flush()
+        for i in range(3):
+            fstep(i)
+        cache.reset()
+        l0 = vlm._lib.launch_count()
+        cache.timing, cache.events = True, []
+        fms, _, _, _ = timed(fstep, args.steps, with_allreduce=True)
+        cache.timing = False
+        l1 = vlm._lib.launch_count()
+        sy_ms = sum(a.elapsed_time(b) for a, b, *_ in cache.events)
+        sy_fl = sum(e[2] for e in cache.events)
+        # parity of one ROW-SLICED Gram (image rows of the joint sequence into the `v` expert) on identical activations
+        cache.reset()
+        probe = {}
+        mod = dict(model.named_modules())["transformer.blocks.3.mlp.v.fc1"]
+        h = mod.register_forward_hook(lambda m, i, o: probe.__setitem__("x", (i[0].is_contiguous(), i[0].double().reshape(-1, i[0].shape[-1]))))
+        fstep(0)
+        h.remove()
+        contiguous, x64 = probe["x"]
+        want = x64.T @ x64
+        err = float(((cache.gram("transformer.blocks.3.mlp.v.fc1").double() - want).norm() / want.norm()).item())
+        fused = {"value": round(world * B * args.steps / (fms * 1e-3), 2), "unit": "samples/s",
+                 "ms_per_step": round(fms / args.steps, 3), "gpu_launches": int(l1 - l0),
+                 "syrk_tflops": round(sy_fl / (sy_ms * 1e-3) * 1e-12, 1) if sy_ms > 0 else None,
+                 "syrk_share_of_step": round(sy_ms / fms, 4), "grams": len(cache.live_names()),
+                 "sliced_input_was_contiguous": bool(contiguous), "sliced_gram_rel_fro": err,
+                 "note": "model.infer: 40 text + 577 image tokens in one sequence; layers < vlffn_start feed row slices to "
+                         "the l / v experts (read in place, 4-D TMA), layers >= vlffn_start run the vl experts"}
         cache.reset()
 
     irtr = bench_irtr(vlm, model, cfg, dev, group, world, args) if args.irtr else None
@@ -366,7 +404,7 @@ def run_ours(args):
                                       "from the hook") if args.defer_mb > 0 else "one SYRK launch per hook call",
                        "allreduce_ms_in_timed_region": round(ar_ms, 3)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "merge": merge, "regmean": regmean, "irtr": irtr, "gram_parity_rel_fro": parity,
+            "roofline": roofline, "merge": merge, "regmean": regmean, "gram_file": gram_file, "fused_route": fused, "irtr": irtr, "gram_parity_rel_fro": parity,
             "forward_variants": variants,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -625,6 +663,41 @@ def run_reference(args):
     return out
 
 
+def bench_gramfile(vlm, cache, dev):
+    """the Gram artefact on disk.  The reference's format (torch.save of full fp64 matrices,
+    cache_gram_matrices.py:349 / vilt_module.py:386) against the packed fp32 upper-triangle container, both written
+    from the same device cache and read back onto the device."""
+    import shutil
+    import tempfile
+
+    tmp = tempfile.mkdtemp(prefix="vlm_gram_")
+    ref, packed = os.path.join(tmp, "grams.pth"), os.path.join(tmp, "grams.vlmgram")
+    try:
+        torch.cuda.synchronize(dev)
+        t = time.perf_counter()
+        cache.save(ref)
+        t_ref_save = time.perf_counter() - t
+        t = time.perf_counter()
+        nbytes = cache.save_packed(packed)
+        t_packed_save = time.perf_counter() - t
+        t = time.perf_counter()
+        g_ref = {k: v.to(dev) for k, v in torch.load(ref, map_location="cpu", weights_only=False).items()}
+        torch.cuda.synchronize(dev)
+        t_ref_load = time.perf_counter() - t
+        t = time.perf_counter()
+        g_packed = vlm.gramfile.load_packed(packed, dev)
+        torch.cuda.synchronize(dev)
+        t_packed_load = time.perf_counter() - t
+        same = all(torch.equal(g_packed[k].double(), g_ref[k]) for k in list(g_ref)[:8])
+        return {"reference_format": {"bytes": os.path.getsize(ref), "save_seconds": round(t_ref_save, 3),
+                                     "load_to_device_seconds": round(t_ref_load, 3)},
+                "packed_fp32_upper": {"bytes": nbytes, "save_seconds": round(t_packed_save, 3),
+                                      "load_to_device_seconds": round(t_packed_load, 3)},
+                "identical_values": bool(same), "grams": len(g_ref)}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -644,6 +717,9 @@ def main():
                          "activations) are grouped into shared launches; 0 = one launch per hook call")
     ap.add_argument("--defer-cap-mb", type=int, default=1024, help="flush grouped launches once this much is pending")
     ap.add_argument("--no-regmean", action="store_true")
+    ap.add_argument("--no-gramfile", action="store_true", help="skip timing the Gram file formats (writes ~2.7 GB to a temp dir)")
+    ap.add_argument("--fused", action="store_true",
+                    help="also time Gram caching on the fused vision-language route (model.infer, type_id 2: row-sliced activations)")
     ap.add_argument("--irtr", action="store_true",
                     help="also run config 4: modality-arithmetic merge + IRTR forward over 5k synthetic images x 25k captions")
     ap.add_argument("--no-cpu-baseline", action="store_true")

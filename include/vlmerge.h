@@ -94,6 +94,15 @@ int vlm_syrk_accum_simt(const void* x, int dtype, int64_t rows, int d, int64_t l
  * file (src/cache_gram_matrices.py:251,349). */
 int vlm_sym_finalize(float* g, int d, int64_t ldg, double* out_f64, int64_t ld64, void* stream);
 
+/* Packed form of a Gram for the on-disk container (vl-merging_b200/gramfile.py; replaces the 2.15 GB fp64 pickle
+ * of src/cache_gram_matrices.py:349 <-> src/vilt/modules/vilt_module.py:386 with 0.54 GB): row-major upper
+ * triangle, row r = columns r..d-1 at element offset r*d - r*(r-1)/2, d*(d+1)/2 floats in all.  Only the upper
+ * triangle of g is read (valid before or after vlm_sym_finalize). */
+int vlm_sym_pack_upper(const float* g, int d, int64_t ldg, float* packed, void* stream);
+/* Inverse: the full symmetric d x d matrix, as fp32 (out_dtype VLM_F32) or widened to fp64 (VLM_F64, the
+ * reference's Gram dtype). */
+int vlm_sym_unpack(const float* packed, int d, void* out, int out_dtype, int64_t ldo, void* stream);
+
 /* Host-only view of vlm_syrk_accum's work decomposition for (rows, d) on a device with nsm SMs
  * (elem_bytes 4 = f32, 2 = bf16/f16): writes segments as 5 int32 each {row_block_col0, col_block_col0,
  * width_in_128_blocks, chunk_begin, chunk_end} and ncta+1 offsets into them.  Returns the number of

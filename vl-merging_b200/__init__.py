@@ -1,6 +1,7 @@
 """vl-merging_b200 — B200-native merge hot path of ylsung/vl-merging (import as `vl_merging_b200`).
 
   gram.GramCache                     RegMean Gram caching hook   (src/cache_gram_matrices.py:236-281,349)
+  gramfile                           packed fp32 Gram container <-> the reference's Gram file (:349 / vilt_module.py:386)
   merge.merge_weights / sum_task_vectors / regmean / Merger      (src/vilt/modules/vilt_module.py:366-746)
   checkpoint.modify_checkpoint_vlmo  checkpoint -> merge input (rel-pos table resize) (vilt_module.py:749-806)
   model.VLMo                         stock-torch multiway transformer the hooks hang on
@@ -9,7 +10,7 @@
 Importing the package never touches CUDA; the first compute call loads libvlmerge.so and fails
 loudly if it is missing (there is no CPU fallback).
 """
-from . import _lib, checkpoint, gram, irtr, merge, model, plan  # noqa: F401
+from . import _lib, checkpoint, gram, gramfile, irtr, merge, model, plan  # noqa: F401
 from ._lib import VlmError, build  # noqa: F401
 from .checkpoint import load_checkpoint, modify_checkpoint_vlmo, save_checkpoint  # noqa: F401
 from .gram import GramCache, cache_gram_matrices  # noqa: F401

@@ -269,6 +269,12 @@ class GramCache:
         """torch.save of the reference-format dict (src/cache_gram_matrices.py:349)."""
         torch.save(self.state_dict(), path)
 
+    def save_packed(self, path):
+        """The packed fp32 upper-triangle container (gramfile.py): a quarter of the reference file's bytes;
+        regmean reads either format.  Returns the number of bytes written."""
+        from . import gramfile
+        return gramfile.save_packed(self, path)
+
     def reset(self):
         self._pending, self._pending_bytes = [], 0
         for g in self.buffers.values():

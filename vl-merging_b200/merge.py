@@ -18,7 +18,7 @@ from types import SimpleNamespace
 
 import torch
 
-from . import _lib
+from . import _lib, gramfile
 from .plan import MEAN, SEQ_LERP, WSUM, is_passthrough_key, plan_merge_weights, plan_regmean, plan_sum_task_vectors
 
 _ALIGN = 4  # elements: keeps every arena segment 16-byte aligned for the 128-bit path
@@ -284,7 +284,11 @@ def regmean(state_dict, config, device=None, num_layers=12, group=None, stats=No
 
     device = _resolve_device(state_dict, device)
     lib = _lib.lib()
-    grams = _as_gram_dict(gram_matrices if gram_matrices is not None else _load(config["gram_matrices"]))
+    if gram_matrices is None:
+        gpath = config["gram_matrices"]
+        # the packed fp32 container of gramfile.py, or the reference's own pickle of fp64 matrices
+        gram_matrices = gramfile.load_packed(gpath, device) if gramfile.is_packed_file(gpath) else _load(gpath)
+    grams = _as_gram_dict(gram_matrices)
     alpha = float(config["scaling_for_non_diag"])
     ops = plan_regmean(state_dict.keys(), grams.keys(), config, num_layers)
     todo = [op for op in ops if not op.passthrough]
