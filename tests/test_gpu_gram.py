@@ -151,6 +151,30 @@ def test_deferred_hooks_flush_after_each_forward():
     assert worst < 1e-6, worst
 
 
+@pytest.mark.parametrize("defer", [0, 1 << 40])
+def test_side_stream_mode_matches_in_stream_launches(defer):
+    """GramCache(side_stream=True): launches on a second stream, joined by flush() after every forward; the
+    activations are freed by the forward long before the join, so this also exercises the keep-alive list."""
+    cfg = vlm.vlmo_config("tiny")
+    model = vlm.init_synthetic_(vlm.VLMo(cfg).eval(), seed=1).cuda()
+    a, b = vlm.GramCache(), vlm.GramCache(defer_bytes=defer, side_stream=True)
+    a.register(model)
+    b.register(model)
+    with torch.no_grad():
+        for seed in (3, 4, 5):
+            model(vlm.synthetic_batch(3, cfg, seed=seed, device="cuda", pad=True))
+            model.infer(vlm.synthetic_batch(2, cfg, seed=seed + 10, device="cuda"))   # not model.__call__: no auto flush
+            torch.empty(64 << 20, device="cuda").fill_(float("nan"))                   # churn the allocator
+    assert not b._pending or defer
+    ga, gb = a.state_dict(), b.state_dict()                     # state_dict() flushes and joins
+    assert not b._side_keep and not b._pending
+    assert list(ga) == list(gb)
+    worst = max(((ga[k] - gb[k]).norm() / ga[k].norm()).item() for k in ga)
+    assert worst < 1e-6, worst
+    b.set_side_stream(False)
+    assert b._side is None
+
+
 def test_randomised_shape_sweep():
     """Seeded sweep over ragged shapes and dtypes: whole and partial 128-column blocks, row counts around the
     pipeline chunk (32 / 64 rows), widths that take the CTA-pair kernel (whole 128-byte groups) and widths that

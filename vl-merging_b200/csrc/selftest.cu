@@ -520,6 +520,15 @@ int main(int argc, char** argv) {
     else syrk_case<__half>("case f16", VLM_F16, rows, d, mode, false, iters, 1e-4);
     return g_fail;
   }
+  if (argc >= 9 && !strcmp(argv[1], "strided")) {  // selftest strided <f32|bf16> <nseg> <n_tok> <off> <seg_rows> <d> <iters>
+    const int nseg = atoi(argv[3]), n_tok = atoi(argv[4]), off = atoi(argv[5]), seg_rows = atoi(argv[6]);
+    const int d = atoi(argv[7]), iters = atoi(argv[8]);
+    if (!strcmp(argv[2], "f32"))
+      syrk_strided_case<float>("strided f32", VLM_F32, nseg, n_tok, off, seg_rows, d, false, iters, 2e-4);
+    else
+      syrk_strided_case<__nv_bfloat16>("strided bf16", VLM_BF16, nseg, n_tok, off, seg_rows, d, false, iters, 2e-4);
+    return g_fail;
+  }
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   printf("device: %s, %d SMs, cc %d.%d, vlm abi %d\n", prop.name, prop.multiProcessorCount, prop.major, prop.minor,

@@ -83,7 +83,8 @@ class GramCache:
     at their first call get individual buffers.
     """
 
-    def __init__(self, device=None, use_simt=False, defer_bytes=0, max_pending=256, max_pending_bytes=1 << 30):
+    def __init__(self, device=None, use_simt=False, defer_bytes=0, max_pending=256, max_pending_bytes=1 << 30,
+                 side_stream=False):
         """defer_bytes > 0: an activation of at most that many bytes is not launched on its own (the Gram of a
         40-token text batch is launch-bound: ~7 us of fixed cost for ~2 us of tensor-core work, and a 768-wide
         image Gram exposes its prologue and final epilogue); the hook keeps a REFERENCE to it (no copy) and
@@ -93,7 +94,12 @@ class GramCache:
         Only safe when nothing modifies a hooked activation in place after the hooked module ran — true for the
         VLMo blocks (LayerNorm / attention / GELU outputs are fresh tensors); the default 0 keeps the
         reference's immediate semantics.  Deferred activations stay allocated until the flush; a flush is forced
-        after max_pending activations or max_pending_bytes of them."""
+        after max_pending activations or max_pending_bytes of them.
+        side_stream=True: the SYRK launches go to a second CUDA stream (ordered after the producer of each
+        activation by an event), so they overlap the rest of the forward — its LayerNorm / GELU / softmax
+        phases leave the tensor pipes idle; flush() joins the two streams.  Like deferral it holds a reference to
+        every hooked activation until the next flush() and assumes nothing modifies them in place; register()
+        flushes after every forward of the registered model."""
         self.device = torch.device(device if device is not None else "cuda")
         if self.device.type != "cuda":
             raise RuntimeError("GramCache needs a CUDA device: the Gram hot path has no CPU fallback")
@@ -108,8 +114,10 @@ class GramCache:
         self._handles = []
         self._finalized = True
         self.defer_bytes, self.max_pending, self.max_pending_bytes = int(defer_bytes), int(max_pending), int(max_pending_bytes)
-        self._pending = []     # (dtype code, x2 (kept alive), g, ldx)
+        self._pending = []     # (dtype code, keep-alive tensor, g, ptr, rows, d, ldx, seg_rows, seg_stride)
         self._pending_bytes = 0
+        self._side = torch.cuda.Stream(self.device) if side_stream else None
+        self._side_keep = []   # activations a side-stream launch may still be reading
 
     # ---- the hook -------------------------------------------------------------------------------
     def hook_gram_input(self, module, input, output):
@@ -165,7 +173,7 @@ class GramCache:
             if len(self._pending) >= self.max_pending or self._pending_bytes >= self.max_pending_bytes:
                 self.flush()
             return
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        stream = self._launch_stream(keep)
         if seg_rows:
             _lib.check(self._lib.vlm_syrk_accum_strided(ptr, code, rows, d, ldx, seg_rows, seg_stride, g.data_ptr(),
                                                         g.stride(0), stream))
@@ -173,12 +181,35 @@ class GramCache:
             fn = self._lib.vlm_syrk_accum_simt if simt else self._fn
             _lib.check(fn(ptr, code, rows, d, ldx, g.data_ptr(), g.stride(0), stream))
 
+    def _launch_stream(self, keep=None):
+        """Raw handle of the stream a SYRK launch goes to.  Side-stream mode: the side stream, made to wait for
+        everything queued so far on the current stream (the activation's producer); `keep` stays referenced until
+        the join in flush()."""
+        cur = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            return cur.cuda_stream
+        self._side.wait_stream(cur)
+        if keep is not None:
+            self._side_keep.append(keep)
+        return self._side.cuda_stream
+
+    def set_side_stream(self, enabled):
+        """Switch side-stream mode on or off between forwards (joins first)."""
+        self.flush()
+        self._side = torch.cuda.Stream(self.device) if enabled else None
+
+    def _join(self):
+        if self._side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
+            self._side_keep = []
+
     def flush(self):
-        """Issue every deferred activation: one grouped launch per dtype on the current stream."""
+        """Issue every deferred activation (one grouped launch per dtype) and, in side-stream mode, make the
+        current stream wait for the Gram launches."""
         if not self._pending:
-            return
+            return self._join()
         pending, self._pending, self._pending_bytes = self._pending, [], 0
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        stream = self._launch_stream()
         for code in sorted({p[0] for p in pending}):
             group = [p for p in pending if p[0] == code]
             probs = (_lib.SyrkProblem * len(group))()
@@ -186,6 +217,7 @@ class GramCache:
                 q.x, q.rows, q.ldx, q.g, q.ldg, q.d = ptr, rows, ldx, g.data_ptr(), g.stride(0), d
                 q.seg_rows, q.seg_stride = seg_rows, seg_stride
             _lib.check(self._lib.vlm_syrk_accum_batch(probs, len(group), code, stream))
+        self._join()
         # `pending` (and with it the activations) is released here: the launches are already ordered on the stream
 
     # ---- registration ---------------------------------------------------------------------------
@@ -199,7 +231,7 @@ class GramCache:
             self._handles.append(module.register_forward_hook(self.hook_gram_input))
             picked.append((name, _in_features(module)))
         self._allocate_arena([(n, d) for n, d in picked if d is not None and n not in self.buffers])
-        if self.defer_bytes > 0:
+        if self.defer_bytes > 0 or self._side is not None:
             self._handles.append(model.register_forward_hook(lambda m, i, o: self.flush()))
         return [n for n, _ in picked]
 
@@ -277,6 +309,7 @@ class GramCache:
 
     def reset(self):
         self._pending, self._pending_bytes = [], 0
+        self._join()
         for g in self.buffers.values():
             g.zero_()
         self.calls.clear()
