@@ -55,38 +55,62 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// L2 eviction policies (createpolicy): the activation X is a stream that is only re-read within a short window
+// (by the other clusters sweeping the same rows), the Gram tiles are re-read and re-written by every K segment's
+// reduce-add for the whole launch.
+__device__ __forceinline__ uint64_t l2_policy(int kind) {  // 0 evict_normal, 1 evict_first, 2 evict_last
+  uint64_t p;
+  if (kind == 1)
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else if (kind == 2)
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 // one box of a 3-D tensor map; lands in this CTA only
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint64_t* bar, void* smem_dst, int c0, int c1,
-                                            int c2) {
+                                            int c2, uint64_t pol) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "l"(pol)
       : "memory");
 }
 // same, delivered to the same smem offset (and signalling the same mbarrier offset) in every CTA of `mask`
 __device__ __forceinline__ void tma_load_3d_mcast(const CUtensorMap* tm, uint64_t* bar, void* smem_dst, int c0,
-                                                  int c1, int c2, uint16_t mask) {
+                                                  int c1, int c2, uint16_t mask, uint64_t pol) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%4, %5, %6}], [%2], %3;" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2)
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+      " [%0], [%1, {%4, %5, %6}], [%2], %3, %7;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
       : "memory");
 }
 // 4-D variants for row-SEGMENTED activations {column in group, row in segment, column group, segment}
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint64_t* bar, void* smem_dst, int c0, int c1,
-                                            int c2, int c3) {
+                                            int c2, int c3, uint64_t pol) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
-      "r"(c3)
+      "r"(c3), "l"(pol)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_4d_mcast(const CUtensorMap* tm, uint64_t* bar, void* smem_dst, int c0,
-                                                  int c1, int c2, int c3, uint16_t mask) {
+                                                  int c1, int c2, int c3, uint16_t mask, uint64_t pol) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%4, %5, %6, %7}], [%2], %3;" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+      " [%0], [%1, {%4, %5, %6, %7}], [%2], %3, %8;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+      "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d_hint(const CUtensorMap* tm, const void* smem_src, int c0, int c1,
+                                                       uint64_t pol) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+      ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(pol)
       : "memory");
 }
 // tcgen05.commit arriving on the mbarrier at this smem offset in every CTA of `mask`
@@ -114,7 +138,7 @@ template <int ELEM_BYTES, int FMT, bool BATCH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_g1,
                 const CUtensorMap* __restrict__ maps, const void* __restrict__ segs_raw,
-                const int* __restrict__ seg_off, int d1, int cps1) {
+                const int* __restrict__ seg_off, int d1, int cps1, int l2_hints) {
   using G = Geo<ELEM_BYTES>;
   using Seg = typename std::conditional<BATCH, BatchSeg, PairSeg>::type;
   const Seg* __restrict__ segs = static_cast<const Seg*>(segs_raw);
@@ -183,6 +207,7 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     int cur_pid = -1;
+    const uint64_t pol_x = l2_policy(l2_hints & 3);
     for (int s = seg_begin; s < seg_end; ++s) {
       const Seg seg = segs[s];
       const CUtensorMap* tm_x = map_x(seg);
@@ -207,11 +232,11 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant
         uint8_t* sb = stage_base + stage * kStageB;
         const int row = kin * kRows;
         if (cps > 0) {
-          tma_load_4d_mcast(tm_x, &full[stage], sb + rank * kBlk, 0, row, b_group, xseg, (uint16_t)0x3);
-          if (!diag) tma_load_4d(tm_x, &full[stage], sb + 2 * kBlk, 0, row, a_group, xseg);
+          tma_load_4d_mcast(tm_x, &full[stage], sb + rank * kBlk, 0, row, b_group, xseg, (uint16_t)0x3, pol_x);
+          if (!diag) tma_load_4d(tm_x, &full[stage], sb + 2 * kBlk, 0, row, a_group, xseg, pol_x);
         } else {
-          tma_load_3d_mcast(tm_x, &full[stage], sb + rank * kBlk, 0, row, b_group, (uint16_t)0x3);
-          if (!diag) tma_load_3d(tm_x, &full[stage], sb + 2 * kBlk, 0, row, a_group);
+          tma_load_3d_mcast(tm_x, &full[stage], sb + rank * kBlk, 0, row, b_group, (uint16_t)0x3, pol_x);
+          if (!diag) tma_load_3d(tm_x, &full[stage], sb + 2 * kBlk, 0, row, a_group, pol_x);
         }
         if (++kin == cps) {
           kin = 0;
@@ -270,6 +295,7 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant
     uint32_t acc_phase = 0;
     uint32_t slab_counter = 0;
     int cur_pid = -1;
+    const uint64_t pol_g = l2_policy((l2_hints >> 2) & 3);
     for (int s = seg_begin; s < seg_end; ++s) {
       const Seg seg = segs[s];
       const CUtensorMap* tm_g = map_g(seg);
@@ -312,7 +338,7 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (epi_tid == 0) {
-          tma_reduce_add_2d(tm_g, buf, col0 + sl * 32, row0);
+          tma_reduce_add_2d_hint(tm_g, buf, col0 + sl * 32, row0, pol_g);
           bulk_commit_group();
         }
         ++slab_counter;
@@ -413,6 +439,15 @@ struct Scratch {
 };
 std::map<std::pair<int, cudaStream_t>, Scratch> g_scratch;
 
+// bits 0-1: policy of the X loads, bits 2-3: policy of the G reduce-adds (0 normal, 1 evict_first, 2 evict_last)
+int l2_hints() {
+  static const int v = [] {
+    const char* e = getenv("VLM_SYRK_L2_HINTS");
+    return e ? atoi(e) : (2 << 2);
+  }();
+  return v;
+}
+
 template <int ELEM_BYTES, int FMT>
 int launch_kernel2(int dev, const DeviceSchedule2& sched, const CUtensorMap& tm_x, const CUtensorMap& tm_g, int d,
                    int cps, cudaStream_t stream) {
@@ -422,7 +457,7 @@ int launch_kernel2(int dev, const DeviceSchedule2& sched, const CUtensorMap& tm_
     VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     if (dev < 64) attr_done[dev].store(true, std::memory_order_release);
   }
-  kernel<<<2 * sched.nclusters, kThreads, kSmemBytes, stream>>>(tm_x, tm_g, nullptr, sched.d_segs, sched.d_off, d, cps);
+  kernel<<<2 * sched.nclusters, kThreads, kSmemBytes, stream>>>(tm_x, tm_g, nullptr, sched.d_segs, sched.d_off, d, cps, l2_hints());
   VLM_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -439,6 +474,10 @@ int launch_kernel2(int dev, const DeviceSchedule2& sched, const CUtensorMap& tm_
 //     left-over tiles are cut along K into C equal shares (stream-K) so that nobody idles;
 //   * T <  C: every tile is cut along K into m = floor(C/T) equal pieces with the SAME boundaries for all
 //     tiles (clusters on different tiles then stay aligned in K); T*m clusters are used.
+// With at least one round, a cluster's left-over pieces are merged into its last sweep next to the own-tile
+// segment covering the same rows (see below), so they too read the band of X that is in L2.  The reduce-adds
+// into G carry an L2 evict_last policy: each tile is re-read and re-written by every K segment while ~45 MB of X
+// stream through L2 in between (ncu, 36928 x 3072 fp32: DRAM read+write 636 MB without either, 526 MB with both).
 // A K range longer than seg_cap chunks is processed as consecutive segments of at most seg_cap chunks:
 // each ends with its own reduce-add into G (hidden behind the next segment's mainloop by the double-
 // buffered TMEM accumulator), which bounds the tensor core's truncating fp32 accumulation.
@@ -491,10 +530,41 @@ void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairS
       const double makespan = (double)((rem * p + C - 1) / C) / (double)p;
       if (makespan < best - 1e-9) best = makespan, best_p = p;
     }
+    // With at least one round of whole tiles, a left-over piece is not appended after the sweep (by then its rows
+    // have long left L2: X is streamed once per round) but INTERLEAVED into the cluster's last sweep, right after
+    // the own-tile segment that covers the same rows — every cluster keeps reading the one band of X that is in L2.
+    std::vector<std::vector<PairSeg>> sweep;
+    static const bool interleave_on = [] {
+      const char* e = getenv("VLM_SYRK_INTERLEAVE");
+      return e ? atoi(e) != 0 : true;
+    }();
+    const bool interleave = interleave_on && rounds > 0;
+    if (interleave) {
+      sweep.resize(C);
+      for (int c = 0; c < C; ++c) {
+        const size_t n_last = (size_t)((kc + seg_cap - 1) / seg_cap);  // segments of the last whole tile
+        sweep[c].assign(per[c].end() - n_last, per[c].end());
+        per[c].resize(per[c].size() - n_last);
+      }
+    }
     int64_t q = 0;
     for (int64_t p = 0; p < best_p; ++p)
       for (int64_t t = 0; t < rem; ++t, ++q)
         emit((int)(q % C), tiles[rounds * C + t], kc * p / best_p, kc * (p + 1) / best_p);
+    if (interleave) {
+      for (int c = 0; c < C; ++c) {
+        // per[c] = earlier rounds + this cluster's left-over pieces (ascending k0); merge them into the sweep
+        const size_t n_before = (size_t)(rounds - 1) * (size_t)((kc + seg_cap - 1) / seg_cap);
+        std::vector<PairSeg> pieces(per[c].begin() + n_before, per[c].end());
+        per[c].resize(n_before);
+        size_t i = 0;
+        for (const PairSeg& own : sweep[c]) {
+          per[c].push_back(own);
+          while (i < pieces.size() && pieces[i].k0 < own.k1) per[c].push_back(pieces[i++]);
+        }
+        while (i < pieces.size()) per[c].push_back(pieces[i++]);
+      }
+    }
   }
   while (!per.empty() && per.back().empty()) per.pop_back();  // clusters without work are not launched
   segs->clear();
@@ -667,7 +737,7 @@ int syrk_tc2_batch_launch(const vlm_syrk_problem* probs, int n, int dtype, cudaS
     VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     kernel<<<2 * ncl, kThreads, kSmemBytes, stream>>>(maps[0], maps[1], reinterpret_cast<const CUtensorMap*>(dptr),
                                                         dptr + maps_bytes + off_bytes,
-                                                        reinterpret_cast<const int*>(dptr + maps_bytes), 0, 0);
+                                                        reinterpret_cast<const int*>(dptr + maps_bytes), 0, 0, l2_hints());
     VLM_CUDA(cudaGetLastError());
     count_launch();
     return 0;
