@@ -163,6 +163,12 @@ int vlm_regmean_rhs(const float* w, int out_f, int in_f, int64_t ldw,
  * Synchronises `stream` to read the factorisation status. */
 int vlm_spd_solve_right(double* s, int in_f, int64_t lds, double* r, int out_f, int64_t ldr,
                         void* stream);
+/* Same without the synchronisation, so that independent solves can run concurrently on several streams
+ * (a Cholesky factorisation of a 768..4096-wide matrix does not fill the GPU on its own): the two status words
+ * (potrf: > 0 = leading minor that is not positive definite; potrs) are written to info_dev[0..1] (device
+ * memory) for the caller to read after its own synchronisation.  One cuSOLVER handle is kept per stream. */
+int vlm_spd_solve_right_async(double* s, int in_f, int64_t lds, double* r, int out_f, int64_t ldr,
+                              int* info_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -86,6 +86,30 @@ def test_singular_gram_sum_raises_like_torch_inverse():
         vlm.regmean(_t(sd), cfg, gram_matrices=_t(bad))
 
 
+@pytest.mark.parametrize("device_inputs", [False, True], ids=["host-inputs", "device-inputs"])
+def test_regmean_concurrent_streams_equal_sequential(device_inputs):
+    """The per-linear problems spread over several streams (default) vs one after the other: same kernels on the
+    same data, bit-identical results; the singular case raises in both modes."""
+    sd, cfg, grams = G.inputs("regmean_s0.9")
+    dev = "cuda" if device_inputs else "cpu"
+    seq = vlm.regmean(_t(sd, dev), cfg, gram_matrices=_t(grams, dev), solve_streams=1)
+    for n in (2, 4, 7):
+        con = vlm.regmean(_t(sd, dev), cfg, gram_matrices=_t(grams, dev), solve_streams=n)
+        assert list(con) == list(seq)
+        for k in seq:
+            assert torch.equal(con[k], seq[k]), (n, k)
+    bad = dict(grams)
+    for k in bad:
+        if k.startswith("transformer.blocks.0.mlp") and k.endswith("fc2"):
+            bad[k] = np.zeros_like(bad[k])
+    sd1, cfg1, _ = G.inputs("regmean_s1.0")
+    for n in (1, 4):
+        with pytest.raises(torch.linalg.LinAlgError):
+            vlm.regmean(_t(sd1, dev), cfg1, gram_matrices=_t(bad, dev), solve_streams=n)
+    ok = vlm.regmean(_t(sd, dev), cfg, gram_matrices=_t(grams, dev))        # and the library is healthy afterwards
+    assert all(torch.equal(ok[k], seq[k]) for k in seq)
+
+
 # ---- properties at the VLMo-base size (184 M expert parameters on the device) ---------------------
 
 @pytest.fixture(scope="module")

@@ -10,7 +10,9 @@
 // rounding), so the scaled Gram is never materialised.
 #include <dlfcn.h>
 
+#include <map>
 #include <mutex>
+#include <utility>
 
 #include "common.cuh"
 
@@ -212,7 +214,6 @@ struct Cusolver {
   cusolverStatus_t (*potrf_bufsize)(cusolverDnHandle_t, int, int, double*, int, int*) = nullptr;
   cusolverStatus_t (*potrf)(cusolverDnHandle_t, int, int, double*, int, double*, int, int*) = nullptr;
   cusolverStatus_t (*potrs)(cusolverDnHandle_t, int, int, int, const double*, int, double*, int, int*) = nullptr;
-  cusolverDnHandle_t handle[64] = {};
 };
 Cusolver g_cs;
 std::mutex g_cs_mu;
@@ -302,20 +303,32 @@ extern "C" int vlm_regmean_rhs(const float* w, int out_f, int in_f, int64_t ldw,
   return 0;
 }
 
-extern "C" int vlm_spd_solve_right(double* s, int in_f, int64_t lds, double* r, int out_f, int64_t ldr,
-                                   void* stream) {
-  VLM_REQUIRE(s && r && in_f > 0 && out_f > 0 && lds >= in_f && ldr >= in_f, VLM_ERR_INVALID_ARG,
-              "vlm_spd_solve_right: bad arguments");
+namespace {
+// One cuSOLVER handle per (device, stream): a handle owns a cuBLAS handle and workspace, so concurrent solves on
+// different streams must not share one.
+std::map<std::pair<int, cudaStream_t>, cusolverDnHandle_t> g_cs_handles;
+
+// potrf + potrs on `st`; info_dev[0..1] receive the two LAPACK-style status words.  `work_out` (stream-ordered
+// allocation) is returned for the caller to free after the solve has been enqueued.
+int enqueue_spd_solve(double* s, int in_f, int64_t lds, double* r, int out_f, int64_t ldr, int* info_dev,
+                      cudaStream_t st) {
   int dev = 0;
   VLM_CUDA(cudaGetDevice(&dev));
-  VLM_REQUIRE(dev < 64, VLM_ERR_UNSUPPORTED, "device index %d out of range", dev);
-  auto st = static_cast<cudaStream_t>(stream);
-  std::lock_guard<std::mutex> lk(g_cs_mu);
-  if (int rc = load_cusolver()) return rc;
-  if (!g_cs.handle[dev])
-    VLM_REQUIRE(g_cs.create(&g_cs.handle[dev]) == 0, VLM_ERR_DRIVER, "cusolverDnCreate failed");
-  cusolverDnHandle_t h = g_cs.handle[dev];
-  VLM_REQUIRE(g_cs.set_stream(h, st) == 0, VLM_ERR_DRIVER, "cusolverDnSetStream failed");
+  cusolverDnHandle_t h = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_cs_mu);
+    if (int rc = load_cusolver()) return rc;
+    auto key = std::make_pair(dev, st);
+    auto it = g_cs_handles.find(key);
+    if (it == g_cs_handles.end()) {
+      VLM_REQUIRE(g_cs_handles.size() < 256, VLM_ERR_UNSUPPORTED, "too many distinct streams use vlm_spd_solve_right");
+      VLM_REQUIRE(g_cs.create(&h) == 0, VLM_ERR_DRIVER, "cusolverDnCreate failed");
+      VLM_REQUIRE(g_cs.set_stream(h, st) == 0, VLM_ERR_DRIVER, "cusolverDnSetStream failed");
+      g_cs_handles.emplace(key, h);
+    } else {
+      h = it->second;
+    }
+  }
   // Row-major symmetric S is also column-major S.  Row-major R (out_f x in_f) read column-major is
   // R^T (in_f x out_f), and S * X^T = R^T  <=>  X = R * S^{-1}: potrs leaves X row-major in r.
   const int uplo_lower = 0;  // CUBLAS_FILL_MODE_LOWER
@@ -323,19 +336,40 @@ extern "C" int vlm_spd_solve_right(double* s, int in_f, int64_t lds, double* r, 
   VLM_REQUIRE(g_cs.potrf_bufsize(h, uplo_lower, in_f, s, (int)lds, &lwork) == 0, VLM_ERR_DRIVER,
               "cusolverDnDpotrf_bufferSize failed");
   double* work = nullptr;
-  int* info = nullptr;
   VLM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&work), sizeof(double) * (size_t)std::max(lwork, 1), st));
-  VLM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&info), sizeof(int) * 2, st));
-  cusolverStatus_t cs1 = g_cs.potrf(h, uplo_lower, in_f, s, (int)lds, work, lwork, info);
-  cusolverStatus_t cs2 = g_cs.potrs(h, uplo_lower, in_f, out_f, s, (int)lds, r, (int)ldr, info + 1);
+  cusolverStatus_t cs1 = g_cs.potrf(h, uplo_lower, in_f, s, (int)lds, work, lwork, info_dev);
+  cusolverStatus_t cs2 = g_cs.potrs(h, uplo_lower, in_f, out_f, s, (int)lds, r, (int)ldr, info_dev + 1);
   count_launch(2);
-  int info_host[2] = {0, 0};
-  cudaError_t e = cudaMemcpyAsync(info_host, info, sizeof(info_host), cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cudaFreeAsync(work, st);
-  cudaFreeAsync(info, st);
-  if (e != cudaSuccess) return fail((int)e, "vlm_spd_solve_right: %s", cudaGetErrorString(e));
   VLM_REQUIRE(cs1 == 0 && cs2 == 0, VLM_ERR_INTERNAL, "cuSOLVER potrf/potrs status %d/%d", cs1, cs2);
+  return 0;
+}
+}  // namespace
+
+extern "C" int vlm_spd_solve_right_async(double* s, int in_f, int64_t lds, double* r, int out_f, int64_t ldr,
+                                         int* info_dev, void* stream) {
+  VLM_REQUIRE(s && r && info_dev && in_f > 0 && out_f > 0 && lds >= in_f && ldr >= in_f, VLM_ERR_INVALID_ARG,
+              "vlm_spd_solve_right_async: bad arguments");
+  return enqueue_spd_solve(s, in_f, lds, r, out_f, ldr, info_dev, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vlm_spd_solve_right(double* s, int in_f, int64_t lds, double* r, int out_f, int64_t ldr,
+                                   void* stream) {
+  VLM_REQUIRE(s && r && in_f > 0 && out_f > 0 && lds >= in_f && ldr >= in_f, VLM_ERR_INVALID_ARG,
+              "vlm_spd_solve_right: bad arguments");
+  auto st = static_cast<cudaStream_t>(stream);
+  int* info = nullptr;
+  VLM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&info), sizeof(int) * 2, st));
+  const int rc = enqueue_spd_solve(s, in_f, lds, r, out_f, ldr, info, st);
+  int info_host[2] = {0, 0};
+  cudaError_t e = cudaSuccess;
+  if (rc == 0) {
+    e = cudaMemcpyAsync(info_host, info, sizeof(info_host), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  }
+  cudaFreeAsync(info, st);
+  if (rc != 0) return rc;
+  if (e != cudaSuccess) return fail((int)e, "vlm_spd_solve_right: %s", cudaGetErrorString(e));
   VLM_REQUIRE(info_host[0] == 0, VLM_ERR_NOT_SPD,
               "summed Gram is not positive definite (leading minor %d); calibrate with more rows than "
               "features or use scaling_for_non_diag < 1",

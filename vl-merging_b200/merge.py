@@ -269,6 +269,63 @@ def sum_task_vectors(state_dict, config, device=None, num_layers=12, group=None,
     return _assemble(state_dict, ops, computed)
 
 
+_SOLVE_STREAMS = {}   # device -> side streams of the concurrent RegMean path (libvlmerge keeps one cuSOLVER handle per stream)
+
+
+def _regmean_linears_concurrent(lib, state_dict, grams, lin_ops, mine, cost, alpha, device, n_streams, results):
+    """The linear problems `mine` of regmean() on n_streams CUDA streams (largest first, each to the least
+    loaded stream): per problem vlm_gram_scale_accum + vlm_regmean_rhs per expert, then vlm_spd_solve_right_async.
+    One status read at the end; raises like the sequential path."""
+    cur = torch.cuda.current_stream(device)
+    pool = _SOLVE_STREAMS.setdefault(device, [])
+    while len(pool) < n_streams:
+        pool.append(torch.cuda.Stream(device))
+    streams = pool[:n_streams]
+    info = torch.zeros(len(lin_ops), 2, dtype=torch.int32, device=device)
+    for st in streams:
+        st.wait_stream(cur)
+    load = [0] * n_streams
+    for idx in sorted(mine, key=lambda i: (-cost(lin_ops[i]), i)):
+        op = lin_ops[idx]
+        k = min(range(n_streams), key=lambda j: (load[j], j))
+        load[k] += cost(op)
+        st = streams[k]
+        out_f, in_f = state_dict[op.regmean[0][0]].shape
+        with torch.cuda.stream(st):
+            acc = torch.empty(out_f, in_f, dtype=torch.float64, device=device)
+            summed = torch.empty(in_f, in_f, dtype=torch.float64, device=device)
+            for n, (wkey, gkey) in enumerate(op.regmean):
+                w = state_dict[wkey].detach().to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+                g = grams[gkey]
+                if g.dtype not in (torch.float64, torch.float32):
+                    g = g.double()
+                g = g.detach().to(device=device, non_blocking=True).contiguous()
+                if tuple(g.shape) != (in_f, in_f):
+                    raise RuntimeError(f"Gram {gkey} has shape {tuple(g.shape)}, expected {(in_f, in_f)}")
+                gdt = _lib.VLM_F64 if g.dtype == torch.float64 else _lib.VLM_F32
+                _lib.check(lib.vlm_gram_scale_accum(g.data_ptr(), gdt, in_f, g.stride(0), alpha, summed.data_ptr(),
+                                                    summed.stride(0), int(n > 0), st.cuda_stream))
+                _lib.check(lib.vlm_regmean_rhs(w.data_ptr(), out_f, in_f, w.stride(0), g.data_ptr(), gdt, g.stride(0),
+                                               alpha, acc.data_ptr(), acc.stride(0), int(n > 0), st.cuda_stream))
+                w.record_stream(st)      # inputs that live on another stream's pool must outlive this launch
+                g.record_stream(st)
+            _lib.check(lib.vlm_spd_solve_right_async(summed.data_ptr(), in_f, summed.stride(0), acc.data_ptr(), out_f,
+                                                     acc.stride(0), info[idx].data_ptr(), st.cuda_stream))
+            acc.record_stream(cur)       # consumed on the caller's stream after the join below
+        results[op.dst] = acc
+    for st in streams:
+        cur.wait_stream(st)
+    status = info.cpu()                  # synchronises the caller's stream, hence all of the above
+    for idx in mine:
+        potrf, potrs = int(status[idx, 0]), int(status[idx, 1])
+        if potrf != 0:                   # the reference's torch.inverse raises on a singular sum too
+            raise torch.linalg.LinAlgError(
+                f"{lin_ops[idx].dst}: summed Gram is not positive definite (leading minor {potrf}); calibrate with "
+                "more rows than features or use scaling_for_non_diag < 1")
+        if potrs != 0:
+            raise RuntimeError(f"{lin_ops[idx].dst}: cusolverDnDpotrs info {potrs}")
+
+
 def _as_gram_dict(grams):
     if hasattr(grams, "state_dict") and hasattr(grams, "buffers"):  # a GramCache: stay on the device, fp32
         grams.finalize()
@@ -276,10 +333,14 @@ def _as_gram_dict(grams):
     return grams
 
 
-def regmean(state_dict, config, device=None, num_layers=12, group=None, stats=None, gram_matrices=None):
+def regmean(state_dict, config, device=None, num_layers=12, group=None, stats=None, gram_matrices=None,
+            solve_streams=4):
     """RegMean merge.  config keys: gram_matrices (path of the Gram file, as in the reference — or pass
     gram_matrices= a dict / GramCache), scaling_for_non_diag, vlffn_start_layer_index, loss_names.
-    Linear weights come back fp64 like the reference's; biases / LayerNorms fp32."""
+    Linear weights come back fp64 like the reference's; biases / LayerNorms fp32.
+    solve_streams: the independent per-linear problems (W*Ghat GEMMs + Cholesky solve) are spread over this many
+    CUDA streams — one factorisation does not fill the GPU; 1 = strictly sequential (and the only mode in which
+    `stats` receives the rhs / solve time split)."""
     import torch.distributed as dist
 
     device = _resolve_device(state_dict, device)
@@ -313,8 +374,15 @@ def regmean(state_dict, config, device=None, num_layers=12, group=None, stats=No
         stream = torch.cuda.current_stream(device).cuda_stream
         results = {}
         t_rhs = t_solve = 0.0
+        mine_lin = [idx for idx in range(len(lin_ops)) if owner[idx] == rank]
+        concurrent = solve_streams > 1 and len(mine_lin) > 1
+        if concurrent:
+            _regmean_linears_concurrent(lib, state_dict, grams, lin_ops, mine_lin, cost, alpha, device,
+                                        min(int(solve_streams), len(mine_lin)), results)
+            if stats is not None:
+                stats["solve_streams"] = min(int(solve_streams), len(mine_lin))
         for idx, op in enumerate(lin_ops):
-            if owner[idx] != rank:
+            if owner[idx] != rank or concurrent:
                 continue
             out_f, in_f = state_dict[op.regmean[0][0]].shape
             acc = torch.empty(out_f, in_f, dtype=torch.float64, device=device)
