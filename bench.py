@@ -404,6 +404,11 @@ def run_ours(args):
 
     irtr = bench_irtr(vlm, model, cfg, dev, group, world, args) if args.irtr else None
 
+    # ---- the reference's own hook, unchanged, with the model on the B200 (the GPU-vs-GPU "before") ----
+    ref_gpu = None
+    if world == 1 and not args.no_gpu_baseline:
+        ref_gpu = bench_reference_hook_on_gpu(vlm, model, cache, dev_batches, B)
+
     out = None
     if rank == 0:
         out = {
@@ -420,7 +425,7 @@ def run_ours(args):
                                       "from the hook") if args.defer_mb > 0 else "one SYRK launch per hook call",
                        "allreduce_ms_in_timed_region": round(ar_ms, 3)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "merge": merge, "regmean": regmean, "gram_file": gram_file, "fused_route": fused, "irtr": irtr, "gram_parity_rel_fro": parity,
+            "roofline": roofline, "merge": merge, "reference_hook_on_gpu": ref_gpu, "regmean": regmean, "gram_file": gram_file, "fused_route": fused, "irtr": irtr, "gram_parity_rel_fro": parity,
             "forward_variants": variants,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -571,10 +576,12 @@ def bench_regmean(vlm, model, cfg, cache, dev, group, world, args):
         torch.cuda.synchronize(dev)
         return time.perf_counter() - t0, stats, out
 
+    NS = 8
     run(1)                      # warm-up of the sequential path too
-    runs = [run(4) for _ in range(2)]  # best of two: cuSOLVER / lazy module loading can leave stragglers after the warm-up
+    runs = [run(NS) for _ in range(2)]  # best of two: cuSOLVER / lazy module loading can leave stragglers after the warm-up
     dt, _, merged = min(runs, key=lambda r: r[0])
-    dt_seq, stats, merged_seq = run(1)  # sequential: the only mode with a meaningful rhs / solve split
+    # sequential: the only mode with a meaningful rhs / solve split (best of two as well)
+    dt_seq, stats, merged_seq = min((run(1) for _ in range(2)), key=lambda r: r[0])
     same = all(torch.equal(merged[k], merged_seq[k]) for k in merged)
     # check: layer 0 attention projection, torch fp64 on the same device Grams
     a = 0.9
@@ -589,14 +596,14 @@ def bench_regmean(vlm, model, cfg, cache, dev, group, world, args):
     err = ((got - want).norm() / want.norm()).item()
     d, h = cfg["hidden_size"], cfg["hidden_size"] * cfg["mlp_ratio"]
     rhs_flops = L * 2 * 2 * (3 * d * d * d + d * d * d + h * d * d + d * h * h)
-    return {"seconds": round(dt, 4), "seconds_both_runs": [round(r[0], 4) for r in runs], "solve_streams": 4,
+    return {"seconds": round(dt, 4), "seconds_both_runs": [round(r[0], 4) for r in runs], "solve_streams": NS,
             "seconds_sequential": round(dt_seq, 4), "concurrent_equals_sequential": bool(same),
             "rhs_seconds": round(stats.get("rhs_seconds", 0.0), 4),
             "solve_seconds": round(stats.get("solve_seconds", 0.0), 4),
             "rhs_fp64_tflops": round(rhs_flops / max(stats.get("rhs_seconds", 1e-9), 1e-9) * 1e-12 / world, 2),
             "linear_problems": 4 * L, "dtype": "f64", "check_rel_err_vs_torch_fp64": err,
             "note": "RHS = fp64 DMMA kernel incl. scale_G and sum of Grams; solve = cuSOLVER potrf/potrs (off the hot path); "
-                    "seconds = the 48 linear problems spread over 4 streams, rhs/solve split from the sequential run"}
+                    "seconds = the linear problems spread over 8 streams, rhs/solve split from the sequential run"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -687,6 +694,47 @@ def run_reference(args):
     return out
 
 
+def bench_reference_hook_on_gpu(vlm, model, cache, dev_batches, B, steps=3):
+    """What the reference does when its model sits on a GPU (src/cache_gram_matrices.py:246-254, restated here line
+    for line): cast the activation to fp64, one fp64 matmul on the device, a synchronous .cpu() of the d x d result
+    and the accumulation on the host — same stock-torch forward, same batches.  Our hooks are removed for good
+    (this leg runs last)."""
+    from collections import defaultdict
+
+    from vl_merging_b200.gram import select_hooked_modules
+
+    cache.remove_hooks()
+    store = defaultdict(float)
+
+    def hook_gram_input(module, input, output):
+        if isinstance(input, tuple):
+            input = input[0]
+        flatten_input = input.reshape(-1, input.shape[-1]).to(torch.float64)
+        gram = torch.matmul(flatten_input.T, flatten_input)
+        store[module.module_name] += gram.detach().cpu()
+
+    handles = []
+    for name, module in select_hooked_modules(model, use_moe=True):
+        module.module_name = name
+        handles.append(module.register_forward_hook(hook_gram_input))
+    try:
+        with torch.no_grad():
+            model(dev_batches[0])                      # warm-up (cuBLAS fp64 plans, host buffers)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(steps):
+                model(dev_batches[(i + 1) % 2])
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+    finally:
+        for h in handles:
+            h.remove()
+    return {"value": round(B * steps / dt, 2), "unit": "samples/s", "steps": steps, "ms_per_step": round(dt / steps * 1e3, 1),
+            "grams": len(store),
+            "note": "reference hook unchanged (fp64 cast + fp64 matmul on the GPU + .cpu() + host accumulate) on the same "
+                    "stock-torch forward and batches; wall clock, one B200"}
+
+
 def bench_gramfile(vlm, cache, dev):
     """the Gram artefact on disk.  The reference's format (torch.save of full fp64 matrices,
     cache_gram_matrices.py:349 / vilt_module.py:386) against the packed fp32 upper-triangle container, both written
@@ -747,6 +795,7 @@ def main():
     ap.add_argument("--irtr", action="store_true",
                     help="also run config 4: modality-arithmetic merge + IRTR forward over 5k synthetic images x 25k captions")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip timing the reference's fp64 hook with the model on the GPU")
     ap.add_argument("--profile", action="store_true",
                     help="for ncu launch lists: run exactly --warmup + --steps calibration steps and exit (no JSON line)")
     args = ap.parse_args()

@@ -334,7 +334,7 @@ def _as_gram_dict(grams):
 
 
 def regmean(state_dict, config, device=None, num_layers=12, group=None, stats=None, gram_matrices=None,
-            solve_streams=4):
+            solve_streams=8):
     """RegMean merge.  config keys: gram_matrices (path of the Gram file, as in the reference — or pass
     gram_matrices= a dict / GramCache), scaling_for_non_diag, vlffn_start_layer_index, loss_names.
     Linear weights come back fp64 like the reference's; biases / LayerNorms fp32.
