@@ -334,6 +334,14 @@ int syrk_tc_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, f
     auto key = std::make_tuple(dev, kc, d, bk, nsm);
     auto it = g_sched.find(key);
     if (it == g_sched.end()) {
+      if (g_sched.size() >= 512) {  // ragged workloads: start over instead of growing forever
+        VLM_CUDA(cudaDeviceSynchronize());
+        for (auto& kv : g_sched) {
+          cudaFree(kv.second.d_segs);
+          cudaFree(kv.second.d_off);
+        }
+        g_sched.clear();
+      }
       std::vector<SyrkSeg> segs;
       std::vector<int> off;
       build_syrk_schedule(kc, d, nsm, &segs, &off);

@@ -623,6 +623,14 @@ int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, 
     auto key = std::make_tuple(dev, kc, d, bk, nsm);
     auto it = g_sched2.find(key);
     if (it == g_sched2.end()) {
+      if (g_sched2.size() >= 512) {  // ragged workloads (a new row count every call): start over, do not grow forever
+        VLM_CUDA(cudaDeviceSynchronize());  // a launch in flight may still read an old schedule
+        for (auto& kv : g_sched2) {
+          cudaFree(kv.second.d_segs);
+          cudaFree(kv.second.d_off);
+        }
+        g_sched2.clear();
+      }
       std::vector<PairSeg> segs;
       std::vector<int> off;
       build_pair_schedule(kc, d, nsm / 2, &segs, &off);

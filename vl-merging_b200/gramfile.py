@@ -89,10 +89,14 @@ def save_packed(grams, path, rows=None, calls=None, device=None):
     pre = MAGIC + struct.pack("<Q", len(header)) + header
     pad = (-len(pre)) % _ALIGN
     tmp = f"{path}.tmp.{os.getpid()}"
-    with open(tmp, "wb") as f:
-        f.write(pre + b"\0" * pad)
-        f.write(memoryview(host.numpy()).cast("B"))
-    os.replace(tmp, path)
+    try:
+        with open(tmp, "wb") as f:
+            f.write(pre + b"\0" * pad)
+            f.write(memoryview(host.numpy()).cast("B"))
+        os.replace(tmp, path)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
     return len(pre) + pad + 4 * total
 
 
