@@ -300,6 +300,45 @@ static void syrk_strided_case(const char* name, int dtype, int nseg, int n_tok, 
   CK(cudaFree(g3));
 }
 
+// ---- packed upper triangle (sympack.cu) ------------------------------------------------------
+static void pack_case(int d, int pad) {
+  const int64_t ld = d + pad;
+  std::vector<float> h((size_t)d * ld);
+  for (auto& v : h) v = frand();
+  float *g, *packed, *o32;
+  double* o64;
+  const size_t np = (size_t)d * (d + 1) / 2;
+  CK(cudaMalloc(&g, h.size() * 4));
+  CK(cudaMalloc(&packed, np * 4));
+  CK(cudaMalloc(&o32, (size_t)d * ld * 4));
+  CK(cudaMalloc(&o64, (size_t)d * ld * 8));
+  CK(cudaMemcpy(g, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+  VK(vlm_sym_pack_upper(g, d, ld, packed, nullptr));
+  VK(vlm_sym_unpack(packed, d, o32, VLM_F32, ld, nullptr));
+  VK(vlm_sym_unpack(packed, d, o64, VLM_F64, ld, nullptr));
+  CK(cudaDeviceSynchronize());
+  std::vector<float> hp(np), h32((size_t)d * ld);
+  std::vector<double> h64((size_t)d * ld);
+  CK(cudaMemcpy(hp.data(), packed, np * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(h32.data(), o32, h32.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(h64.data(), o64, h64.size() * 8, cudaMemcpyDeviceToHost));
+  size_t bad = 0, k = 0;
+  for (int r = 0; r < d; ++r)
+    for (int c = r; c < d; ++c, ++k) bad += hp[k] != h[(size_t)r * ld + c];
+  for (int r = 0; r < d; ++r)
+    for (int c = 0; c < d; ++c) {
+      const float want = c >= r ? h[(size_t)r * ld + c] : h[(size_t)c * ld + r];
+      bad += h32[(size_t)r * ld + c] != want;
+      bad += h64[(size_t)r * ld + c] != (double)want;
+    }
+  printf("PACK d=%-5d ld=%-5lld mismatches=%zu  %s\n", d, (long long)ld, bad, bad == 0 ? "OK" : "FAIL");
+  if (bad) ++g_fail;
+  CK(cudaFree(g));
+  CK(cudaFree(packed));
+  CK(cudaFree(o32));
+  CK(cudaFree(o64));
+}
+
 // ---- merge ---------------------------------------------------------------------------------
 static void merge_case(const char* name, int mode, int n_src, size_t n, size_t misalign, int iters) {
   std::vector<std::vector<float>> hs(n_src, std::vector<float>(n));
@@ -520,6 +559,10 @@ int main(int argc, char** argv) {
     else syrk_case<__half>("case f16", VLM_F16, rows, d, mode, false, iters, 1e-4);
     return g_fail;
   }
+  if (argc >= 2 && !strcmp(argv[1], "pack")) {  // packed upper-triangle kernels only (for compute-sanitizer)
+    for (int d : {1, 31, 33, 192, 768, 1000}) pack_case(d, d % 2 ? 3 : 0);
+    return g_fail;
+  }
   if (argc >= 9 && !strcmp(argv[1], "strided")) {  // selftest strided <f32|bf16> <nseg> <n_tok> <off> <seg_rows> <d> <iters>
     const int nseg = atoi(argv[3]), n_tok = atoi(argv[4]), off = atoi(argv[5]), seg_rows = atoi(argv[6]);
     const int d = atoi(argv[7]), iters = atoi(argv[8]);
@@ -542,6 +585,8 @@ int main(int argc, char** argv) {
   merge_case("mean2", VLM_MERGE_MEAN, 2, 4099, 0, 0);
   merge_case("mean3-misaligned", VLM_MERGE_MEAN, 3, 70001, 1, 0);
   merge_case("wsum2-misaligned", VLM_MERGE_WSUM, 2, 70001, 3, 0);
+
+  for (int d : {1, 33, 768}) pack_case(d, d % 2 ? 3 : 0);
 
   regmean_case(96, 128, 1.0);
   regmean_case(200, 192, 0.9);
