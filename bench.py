@@ -648,7 +648,7 @@ def cpu_baseline_sample(model_name, budget_s=25.0):
             break
     dt = time.perf_counter() - t0
     return {"value": round(done / dt, 4), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{done} calibration step(s) of 1 sample (577+40 tokens, 96 fp64 Grams) of the same VLMo-{model_name} workload, "
+            "sample": f"{done} calibration step(s) of 1 sample (577+40 tokens, {len(store)} fp64 Grams) of the same VLMo-{model_name} workload, "
                       f"stock forward + reference hook on the host, after 1 warm-up step",
             "cpu_model": cpu_model_name()}
 
@@ -677,7 +677,7 @@ def run_reference(args):
         cpu_reference_step(model, cfg, per_step, 1000 + i, store)
     dt = time.perf_counter() - t0
     v = per_step * args.steps / dt
-    sample = f"{per_step} sample per step (577 image + 40 text tokens, 96 fp64 Grams), VLMo-{args.model} all_moe, host cores only"
+    sample = f"{per_step} sample per step (577 image + 40 text tokens, {192 if args.model == 'large' else 96} fp64 Grams), VLMo-{args.model} all_moe, host cores only"
     out = {
         "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True,
