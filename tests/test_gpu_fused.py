@@ -84,6 +84,11 @@ def test_unaligned_or_odd_slices_fall_back_correctly():
         cache = vlm.GramCache()
         cache.accumulate("s", x)
         assert _rel(cache.state_dict()["s"].numpy(), _oracle_gram(x)) < 1e-3
+    # broadcast batch dimension (stride 0): not a segment layout TMA can describe -> the generic copy path
+    e = torch.randn(1, 40, 768, device="cuda").expand(4, 40, 768)
+    cache = vlm.GramCache()
+    cache.accumulate("e", e)
+    assert _rel(cache.state_dict()["e"].numpy(), _oracle_gram(e)) < 1e-3
     # permuted (not a row slice): the generic copy path
     p = torch.randn(64, 8, 128, device="cuda").permute(1, 0, 2)
     cache = vlm.GramCache()

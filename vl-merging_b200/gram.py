@@ -142,7 +142,7 @@ class GramCache:
         except RuntimeError:
             x2 = None
         if x2 is None and x.dim() == 3 and x.stride(2) == 1 and x.stride(1) >= d and x.shape[0] > 1 \
-                and (x.stride(0) * elem) % 16 == 0 and x.stride(0) >= 0:
+                and (x.stride(0) * elem) % 16 == 0 and x.stride(0) > 0:
             # a row slice h[:, a:b] of a (B, N, D) activation (the fused vision-language route hands these to the
             # per-modality experts): read in place as B row segments, where the reference's reshape copies
             rows, ldx, seg_rows, seg_stride, keep = x.shape[0] * x.shape[1], x.stride(1), x.shape[1], x.stride(0), x
