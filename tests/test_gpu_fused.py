@@ -39,7 +39,7 @@ def test_row_slices_are_read_in_place(dtype, d):
     one launch per segment)."""
     torch.manual_seed(d)
     h = torch.randn(6, 40 + 197, d, device="cuda").to(dtype)
-    for lo, hi in ((0, 40), (40, 237), (3, 4)):
+    for lo, hi in ((0, 40), (40, 237), (3, 4), (3, 8)):       # (3, 8): 5-row segments, shorter than one K chunk
         x = h[:, lo:hi]
         assert not x.is_contiguous()
         cache = vlm.GramCache()
