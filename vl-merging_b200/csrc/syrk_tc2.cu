@@ -248,41 +248,56 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===== MMA issuer =====
+    // The WHOLE warp walks the loop and one elected lane issues: with warp-uniform control flow the descriptors
+    // live in uniform registers.  (Issued from inside an `if (lane == 0)` region every tcgen05.mma cost ~23 SASS
+    // instructions of ELECT / R2UR.BROADCAST / descriptor arithmetic, and the issue loop took about as long as
+    // the MMAs themselves: ncu showed the issuing warp busy, not waiting, while the tensor pipe idled 16 %.)
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const uint32_t stage0 = smem_u32(stage_base);
+    // descriptor words that never change: high word = SBO | version | layout type, low word = LBO (start address added)
+    constexpr uint32_t kDescHi = (uint32_t)((G::SBO_BYTES >> 4) & 0x3FFF) | (1u << 14) | ((uint32_t)G::LAYOUT_TYPE << 29);
+    constexpr uint32_t kDescLo = (uint32_t)((kBox >> 4) & 0x3FFF) << 16;
     for (int s = seg_begin; s < seg_end; ++s) {
       const Seg seg = segs[s];
-      const bool diag = seg.sa == seg.sb;
+      const int sa_t = __shfl_sync(0xffffffffu, seg.sa, 0), sb_t = __shfl_sync(0xffffffffu, seg.sb, 0);
+      const int k0 = __shfl_sync(0xffffffffu, seg.k0, 0), k1 = __shfl_sync(0xffffffffu, seg.k1, 0);
+      const bool diag = sa_t == sb_t;
       // diagonal super-tile: CTA 1 forms only its diagonal block (B block 1, N = 128)
       const int n_off = (diag && rank == 1) ? 1 : 0;
-      const int w = 2 - n_off;
-      const uint32_t idesc = make_idesc(FMT, 128 * w);
+      const uint32_t idesc = make_idesc(FMT, 128 * (2 - n_off));
       const uint32_t d_tmem = tmem_base + acc * kAccCols;
+      const uint32_t a_off = diag ? rank * kBlk : 2 * kBlk;
+      const uint32_t b_off = n_off * kBlk;
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
-      for (int k = seg.k0; k < seg.k1; ++k) {
+      for (int k = k0; k < k1; ++k) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t sb = smem_u32(stage_base + stage * kStageB);
-        const uint32_t sa = diag ? sb + rank * kBlk : sb + 2 * kBlk;
-        const uint32_t sbn = sb + n_off * kBlk;
+        const uint32_t sb = stage0 + stage * kStageB;
+        const uint32_t alo = (((sb + a_off) & 0x3FFFFu) >> 4) | kDescLo;
+        const uint32_t blo = (((sb + b_off) & 0x3FFFFu) >> 4) | kDescLo;
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < kNumMma; ++kk) {
-          const uint64_t adesc = make_smem_desc<G::LAYOUT_TYPE>(sa + kk * G::KSTEP_BYTES, kBox, G::SBO_BYTES);
-          const uint64_t bdesc = make_smem_desc<G::LAYOUT_TYPE>(sbn + kk * G::KSTEP_BYTES, kBox, G::SBO_BYTES);
-          umma<FMT>(d_tmem, adesc, bdesc, idesc, (k > seg.k0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < kNumMma; ++kk) {
+            const uint64_t adesc = ((uint64_t)kDescHi << 32) | (alo + kk * (G::KSTEP_BYTES >> 4));
+            const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (blo + kk * (G::KSTEP_BYTES >> 4));
+            umma<FMT>(d_tmem, adesc, bdesc, idesc, (k > k0 || kk > 0) ? 1u : 0u);
+          }
+          tc_commit_mcast(&empty[stage], (uint16_t)0x3);  // slot free in BOTH CTAs once these MMAs have read it
         }
-        tc_commit_mcast(&empty[stage], (uint16_t)0x3);  // slot free in BOTH CTAs once these MMAs have read it
+        __syncwarp();
         if (++stage == kNStages) {
           stage = 0;
           phase ^= 1;
         }
       }
-      tc_commit(&tfull[acc]);
+      if (elect_one()) tc_commit(&tfull[acc]);
+      __syncwarp();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
