@@ -125,7 +125,6 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// arrive on an mbarrier once every tcgen05.mma issued so far by this thread has completed
 // one lane of a converged warp
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -138,6 +137,7 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// arrive on an mbarrier once every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
