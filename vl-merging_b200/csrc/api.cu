@@ -86,6 +86,8 @@ extern "C" int vlm_syrk_accum(const void* x, int dtype, int64_t rows, int d, int
     const char* e = getenv("VLM_SYRK_VARIANT");
     return e ? atoi(e) : 2;
   }();
+  if (variant == 4 && syrk_tc2_supported(dtype, d, ldx))
+    return syrk_tc4_launch(x, dtype, rows, d, ldx, 0, 0, g, ldg, static_cast<cudaStream_t>(stream));
   if (variant == 2 && syrk_tc2_supported(dtype, d, ldx))
     return syrk_tc2_launch(x, dtype, rows, d, ldx, 0, 0, g, ldg, static_cast<cudaStream_t>(stream));
   return syrk_tc_launch(x, dtype, rows, d, ldx, g, ldg, static_cast<cudaStream_t>(stream));

@@ -42,6 +42,9 @@ bool syrk_tc2_supported(int dtype, int d, int64_t ldx);
 // seg_rows > 0: X is rows/seg_rows row segments of seg_rows rows, seg_stride elements apart (0: contiguous rows)
 int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
                     float* g, int64_t ldg, cudaStream_t stream);
+// experimental (VLM_SYRK_VARIANT=4): one CTA per 256 x 256 super-tile, two M = 128 instruction streams sharing B
+int syrk_tc4_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
+                    float* g, int64_t ldg, cudaStream_t stream);
 // several independent problems (same dtype) in one grid; every problem must satisfy syrk_tc2_supported
 int syrk_tc2_batch_launch(const vlm_syrk_problem* probs, int n, int dtype, cudaStream_t stream);
 void build_syrk_pair_schedule_host(int64_t kc, int d, int nsm, std::vector<int32_t>* flat, std::vector<int>* off);
