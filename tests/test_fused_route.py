@@ -120,3 +120,26 @@ def test_regmean_on_fused_grams_matches_reference_golden(golden, tiny, calibrate
         ret = ufo.infer(vlm.synthetic_batch(bs, cfg, seed=seed, pad=pad))
     assert np.abs(ret["cls_feats"].numpy() - z[f"merged/{variant}/cls"]).max() < 1e-4
     assert np.abs(ret["raw_cls_feats"].numpy() - z[f"merged/{variant}/raw_cls"]).max() < 2e-4
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("kind", ["all_moe", "ufo"])
+def test_infer_bit_exact_against_imported_reference(kind):
+    """`VLMo.infer` vs the unmodified reference `infer` (vilt_module.py:1071-1156) on the same weights and a ragged
+    batch: identical bits for both the modality-specific and the merged (shared-weight, split attention) layout."""
+    import ref_harness as rh
+
+    cfg = vlm.vlmo_config("tiny", use_moe=(kind == "all_moe"))
+    mine = vlm.init_synthetic_(vlm.VLMo(cfg).eval(), seed=5)
+    ref_cfg = rh.make_config(["task_finetune_irtr_coco_square_randaug_base_image384", kind],
+                             vit="vit_tiny_patch16_224", hidden_size=192, num_heads=3, image_size=224,
+                             load_path="", random_initialization=True, per_gpu_batchsize=2)
+    ref = rh.build_model(ref_cfg)
+    _, unexpected = ref.load_state_dict(mine.state_dict(), strict=False)
+    assert not unexpected
+    batch = vlm.synthetic_batch(3, cfg, seed=17, pad=True)
+    rbatch = dict(batch, image=[batch["image"]] if not isinstance(batch["image"], (list, tuple)) else batch["image"])
+    with torch.no_grad():
+        a, b = ref.infer(rbatch), mine.infer(batch)
+    for key in ("cls_feats", "raw_cls_feats", "text_feats", "image_feats"):
+        assert torch.equal(a[key], b[key]), key

@@ -88,3 +88,52 @@ def test_forward_bit_exact_against_imported_reference(tiny):
             a, b = getattr(ref, fn)(batch), getattr(model, fn)(batch)
             assert torch.equal(a["cls_feats"], b["cls_feats"])
             assert torch.equal(a["raw_cls_feats"], b["raw_cls_feats"])
+
+
+def test_ufo_hook_registration_rule():
+    """use_moe=False (calibrating a modality-agnostic model, cache_gram_matrices.py:276): mlp.fc1, mlp.fc2, attn.proj,
+    norm1, norm2 of every block — LayerNorms included, the fused qkv not."""
+    ufo = vlm.VLMo(vlm.vlmo_config("tiny", use_moe=False))
+    names = [n for n, _ in select_hooked_modules(ufo, use_moe=False)]
+    assert len(names) == 12 * 5
+    assert names[:5] == [f"transformer.blocks.0.{k}" for k in ("attn.proj", "norm1", "mlp.fc1", "mlp.fc2", "norm2")]
+    assert all(vlm.gram._in_features(m) is not None for _, m in select_hooked_modules(ufo, use_moe=False))
+
+
+@pytest.mark.reference
+def test_ufo_model_hooks_and_grams_against_imported_reference():
+    """The reference's registration loop + hook on ITS ufo model vs ours (same weights, same batch): same hooked
+    names in the same order, same Grams (both sides fp64 on the CPU)."""
+    from collections import defaultdict
+
+    import oracle
+    import ref_harness as rh
+
+    cfg = vlm.vlmo_config("tiny", use_moe=False)
+    mine = vlm.init_synthetic_(vlm.VLMo(cfg).eval(), seed=3)
+    ref_cfg = rh.make_config(["task_finetune_irtr_coco_square_randaug_base_image384", "ufo"],
+                             vit="vit_tiny_patch16_224", hidden_size=192, num_heads=3, image_size=224,
+                             load_path="", random_initialization=True, per_gpu_batchsize=2)
+    ref = rh.build_model(ref_cfg)
+    _, unexpected = ref.load_state_dict(mine.state_dict(), strict=False)
+    assert not unexpected
+    ref_store = defaultdict(float)
+    handles = rh.ref_register_gram_hooks(ref, ref_store, use_moe=False)
+    ref_names = [m.module_name for m in ref.modules() if hasattr(m, "module_name")]
+    my_store = oracle.new_gram_store()
+    hook = oracle.reference_hook_torch(my_store)
+    picked = select_hooked_modules(mine, use_moe=False)
+    for name, module in picked:
+        module.module_name = name
+        handles.append(module.register_forward_hook(hook))
+    assert [n for n, _ in picked] == ref_names
+    batch = vlm.synthetic_batch(3, cfg, seed=9, pad=True)
+    with torch.no_grad():
+        for fn in ("infer_image_ft", "infer_text_ft"):
+            a, b = getattr(ref, fn)(batch), getattr(mine, fn)(batch)
+            assert torch.equal(a["cls_feats"], b["cls_feats"])
+    for h in handles:
+        h.remove()
+    assert list(my_store) == list(ref_store) and len(ref_store) == 60
+    for k, g in ref_store.items():
+        assert torch.equal(my_store[k], g), k
