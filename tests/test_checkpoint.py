@@ -41,3 +41,32 @@ def test_resized_checkpoint_loads_and_merges_shapes():
     with torch.no_grad():
         out = model.infer_image_ft(vlm.synthetic_batch(1, cfg384, seed=1))
     assert out["image_feats"].shape == (1, 577, 192)
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("image_size,max_text_len", [(288, 40), (320, 32), (448, 40), (384, 20), (224, 40)])
+def test_modify_checkpoint_vlmo_against_imported_reference(image_size, max_text_len):
+    """More target geometries than the committed golden holds, against the unmodified reference method executed on
+    the spot (vilt_module.py:749-806): same keys in the same order, identical bits."""
+    import ref_harness as rh
+
+    src = vlm.init_synthetic_(vlm.VLMo(vlm.vlmo_config("tiny")).eval(), seed=4)        # "trained" at 224 px, 40 tokens
+    cfg = rh.make_config(["task_finetune_irtr_coco_square_randaug_base_image384", "all_moe"], hidden_size=192,
+                         num_heads=3, load_path="", random_initialization=True, per_gpu_batchsize=2,
+                         vit="vit_tiny_patch16_224", image_size=image_size, max_text_len=max_text_len)
+    ref = rh.build_model(cfg)
+
+    def ckpt():
+        sd = {k: v.clone() for k, v in src.state_dict().items()}
+        sd["text_embeddings.position_ids"] = torch.arange(40).expand((1, -1)).clone()
+        return {"state_dict": sd}
+
+    want = ref.modify_checkpoint_vlmo(ckpt())
+    got = vlm.modify_checkpoint_vlmo(ckpt(), {k: cfg[k] for k in ("image_size", "patch_size", "max_text_len",
+                                                                "max_text_len_of_initckpt")})
+    assert list(got.keys()) == list(want.keys())
+    for k, w in want.items():
+        assert torch.equal(got[k], w), k
