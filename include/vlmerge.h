@@ -37,7 +37,10 @@ typedef enum {
   VLM_ERR_INTERNAL = -6
 } vlm_status;
 
-typedef enum { VLM_F32 = 0, VLM_BF16 = 1, VLM_F16 = 2, VLM_F64 = 3 } vlm_dtype;
+typedef enum {
+  VLM_F32 = 0, VLM_BF16 = 1, VLM_F16 = 2, VLM_F64 = 3,
+  VLM_TF32X2 = 4   /* Gram input only: the {hi, lo} TF32 planes written by vlm_tf32_split */
+} vlm_dtype;
 
 /* ---- library ------------------------------------------------------------------------------- */
 int         vlm_version(void);          /* VLM_ABI_VERSION */
@@ -57,6 +60,17 @@ uint64_t    vlm_launch_count(void);
  * rows == 0 is a no-op. */
 int vlm_syrk_accum(const void* x, int dtype, int64_t rows, int d, int64_t ldx,
                    float* g, int64_t ldg, void* stream);
+
+/* Split-precision ("3xTF32") Gram input for RegMean-grade Grams.  The reference forms X^T X in fp64
+ * (src/cache_gram_matrices.py:251-252) and regmean inverts the sum (src/vilt/modules/vilt_module.py:432-434,
+ * :483-484); one TF32 pass carries 2^-11 of rounding noise per operand, which the inverse amplifies.
+ * vlm_tf32_split writes out[0][r][c] = hi = tf32(x[r][c]) and out[1][r][c] = lo = tf32(x - hi) (out: 2*rows*d
+ * floats, contiguous, 16-byte aligned; x fp32 with row pitch ldx, optionally row-segmented as in
+ * vlm_syrk_accum_strided, seg_rows = 0 for plain rows).  vlm_syrk_accum / vlm_syrk_accum_batch with
+ * dtype = VLM_TF32X2, x = out, ldx = d then accumulate hi'hi + hi'lo + lo'hi: three tensor-core products per
+ * K step on the same TMA / tcgen05 pipeline.  Needs d % 32 == 0 (VLM_ERR_UNSUPPORTED otherwise). */
+int vlm_tf32_split(const float* x, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
+                   float* out, void* stream);
 
 /* Several independent vlm_syrk_accum problems of the same dtype in ONE launch (e.g. the 48 small Grams of the
  * text tower of one forward, which are launch-bound one by one).  Same contract per problem; the activations

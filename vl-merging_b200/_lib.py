@@ -11,7 +11,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libvlmerge.so")
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
-VLM_F32, VLM_BF16, VLM_F16, VLM_F64 = 0, 1, 2, 3
+VLM_F32, VLM_BF16, VLM_F16, VLM_F64, VLM_TF32X2 = 0, 1, 2, 3, 4
 MERGE_WSUM, MERGE_SEQ_LERP, MERGE_MEAN = 0, 1, 2
 MERGE_MAX_SRC = 4
 ERR_NOT_SPD = -5
@@ -56,6 +56,7 @@ SIGNATURES = {
     "vlm_last_error": (c_char_p, []),
     "vlm_launch_count": (c_uint64, []),
     "vlm_syrk_accum": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_int64, c_void_p]),
+    "vlm_tf32_split": (c_int, [c_void_p, c_int64, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "vlm_syrk_accum_batch": (c_int, [POINTER(SyrkProblem), c_int, c_int, c_void_p]),
     "vlm_syrk_accum_strided": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64,
                                        c_void_p]),

@@ -58,8 +58,8 @@ int require_sm100() {
 namespace {
 int check_syrk_args(const char* who, const void* x, int dtype, int64_t rows, int d, int64_t ldx, const float* g,
                     int64_t ldg) {
-  VLM_REQUIRE(dtype == VLM_F32 || dtype == VLM_BF16 || dtype == VLM_F16, VLM_ERR_INVALID_ARG,
-              "%s: dtype must be VLM_F32, VLM_BF16 or VLM_F16 (got %d)", who, dtype);
+  VLM_REQUIRE(dtype == VLM_F32 || dtype == VLM_BF16 || dtype == VLM_F16 || dtype == VLM_TF32X2, VLM_ERR_INVALID_ARG,
+              "%s: dtype must be VLM_F32, VLM_BF16, VLM_F16 or VLM_TF32X2 (got %d)", who, dtype);
   VLM_REQUIRE(rows >= 0 && d > 0, VLM_ERR_INVALID_ARG, "%s: rows=%lld d=%d", who, (long long)rows, d);
   VLM_REQUIRE(g != nullptr && ldg >= d, VLM_ERR_INVALID_ARG, "%s: g is NULL or ldg < d", who);
   VLM_REQUIRE(rows == 0 || (x != nullptr && ldx >= d), VLM_ERR_INVALID_ARG, "%s: x is NULL or ldx < d", who);
@@ -80,15 +80,18 @@ extern "C" int vlm_syrk_accum(const void* x, int dtype, int64_t rows, int d, int
   if (int rc = check_syrk_args("vlm_syrk_accum", x, dtype, rows, d, ldx, g, ldg)) return rc;
   if (rows == 0) return 0;
   if (int rc = require_sm100()) return rc;
-  // VLM_SYRK_VARIANT=1 forces the first-generation (single-CTA) kernel; default is the CTA-pair kernel
+  // VLM_SYRK_VARIANT=1 forces the first-generation (single-CTA) kernel; default is a CTA-pair kernel
   // whenever the activation has whole 128-byte column groups
   static const int variant = [] {
     const char* e = getenv("VLM_SYRK_VARIANT");
-    return e ? atoi(e) : 2;
+    return e ? atoi(e) : 3;
   }();
-  if (variant == 4 && syrk_tc2_supported(dtype, d, ldx))
-    return syrk_tc4_launch(x, dtype, rows, d, ldx, 0, 0, g, ldg, static_cast<cudaStream_t>(stream));
-  if (variant == 2 && syrk_tc2_supported(dtype, d, ldx))
+  if (dtype == VLM_TF32X2) {
+    VLM_REQUIRE(syrk_tc2_supported(dtype, d, ldx), VLM_ERR_UNSUPPORTED,
+                "vlm_syrk_accum: VLM_TF32X2 needs d %% 32 == 0 (got %d); use vlm_syrk_accum_simt on the fp32 activation", d);
+    return syrk_tc2_launch(x, dtype, rows, d, ldx, 0, 0, g, ldg, static_cast<cudaStream_t>(stream));
+  }
+  if (variant != 1 && syrk_tc2_supported(dtype, d, ldx))
     return syrk_tc2_launch(x, dtype, rows, d, ldx, 0, 0, g, ldg, static_cast<cudaStream_t>(stream));
   return syrk_tc_launch(x, dtype, rows, d, ldx, g, ldg, static_cast<cudaStream_t>(stream));
 }
@@ -116,6 +119,8 @@ extern "C" int vlm_syrk_accum_strided(const void* x, int dtype, int64_t rows, in
   if (rows == 0) return 0;
   if (int rc = check_segments("vlm_syrk_accum_strided", dtype, rows, seg_rows, seg_stride)) return rc;
   if (seg_rows == rows) return vlm_syrk_accum(x, dtype, rows, d, ldx, g, ldg, stream);
+  VLM_REQUIRE(dtype != VLM_TF32X2, VLM_ERR_INVALID_ARG,
+              "vlm_syrk_accum_strided: VLM_TF32X2 planes are packed by vlm_tf32_split, they have no row segments");
   if (int rc = require_sm100()) return rc;
   const int elem = dtype == VLM_F32 ? 4 : 2;
   if (tma_addressable(x, elem, ldx, g, ldg) && ((seg_stride * elem) & 15) == 0 && syrk_tc2_supported(dtype, d, ldx))
@@ -140,8 +145,10 @@ extern "C" int vlm_syrk_accum_batch(const vlm_syrk_problem* probs, int n, int dt
     const vlm_syrk_problem& q = probs[p];
     if (int rc = check_syrk_args("vlm_syrk_accum_batch", q.x, dtype, q.rows, q.d, q.ldx, q.g, q.ldg)) return rc;
     if (q.rows == 0) continue;
-    const int elem = dtype == VLM_F32 ? 4 : 2;
-    const bool segmented = q.seg_rows > 0 && q.seg_rows < q.rows;
+    const int elem = (dtype == VLM_F32 || dtype == VLM_TF32X2) ? 4 : 2;
+    const bool segmented = dtype != VLM_TF32X2 && q.seg_rows > 0 && q.seg_rows < q.rows;
+    VLM_REQUIRE(dtype != VLM_TF32X2 || (tma_addressable(q.x, 4, q.ldx, q.g, q.ldg) && syrk_tc2_supported(dtype, q.d, q.ldx)),
+                VLM_ERR_UNSUPPORTED, "vlm_syrk_accum_batch: VLM_TF32X2 needs d %% 32 == 0 and 16-byte aligned planes");
     if (segmented) {
       if (int rc = check_segments("vlm_syrk_accum_batch", dtype, q.rows, q.seg_rows, q.seg_stride)) return rc;
     }
@@ -165,6 +172,20 @@ extern "C" int vlm_syrk_accum_simt(const void* x, int dtype, int64_t rows, int d
   if (int rc = check_syrk_args("vlm_syrk_accum_simt", x, dtype, rows, d, ldx, g, ldg)) return rc;
   if (rows == 0) return 0;
   return syrk_simt_launch(x, dtype, rows, d, ldx, g, ldg, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vlm_tf32_split(const float* x, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
+                              float* out, void* stream) {
+  VLM_REQUIRE(rows >= 0 && d > 0 && d % 4 == 0 && out != nullptr && (rows == 0 || (x != nullptr && ldx >= d)),
+              VLM_ERR_INVALID_ARG, "vlm_tf32_split: bad arguments (rows=%lld d=%d)", (long long)rows, d);
+  VLM_REQUIRE(seg_rows >= 0 && seg_stride >= 0 && (seg_rows == 0 || rows % seg_rows == 0), VLM_ERR_INVALID_ARG,
+              "vlm_tf32_split: rows (%lld) must be a multiple of seg_rows (%lld)", (long long)rows, (long long)seg_rows);
+  VLM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ldx & 3) == 0 && (seg_stride & 3) == 0 &&
+                  (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+              VLM_ERR_ALIGNMENT, "vlm_tf32_split: x / out must be 16-byte aligned, ldx and seg_stride multiples of 4");
+  if (rows == 0) return 0;
+  if (int rc = require_sm100()) return rc;
+  return tf32_split_launch(x, rows, d, ldx, seg_rows, seg_stride, out, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vlm_sym_finalize(float* g, int d, int64_t ldg, double* out_f64, int64_t ld64, void* stream) {

@@ -224,6 +224,75 @@ static void syrk_case(const char* name, int dtype, int64_t rows, int d, int mode
   CK(cudaFree(g_ref));
 }
 
+
+// Split-precision Gram (vlm_tf32_split + VLM_TF32X2): host fp64 Gram of the whole matrix (host_ref) or of 12
+// sample rows; optionally a row-segmented source (nseg > 1: rows = nseg * seg_rows out of n_tok-row items).
+static void syrk_split_case(const char* name, int nseg, int n_tok, int off, int seg_rows, int d, int mode, bool host_ref,
+                            int iters, double tol) {
+  std::vector<float> hx((size_t)nseg * n_tok * d);
+  fill_x<float>(hx, mode);
+  const int64_t rows = (int64_t)nseg * seg_rows;
+  float *dx, *planes, *g;
+  CK(cudaMalloc(&dx, hx.size() * 4));
+  CK(cudaMalloc(&planes, (size_t)2 * rows * d * 4));
+  CK(cudaMalloc(&g, (size_t)d * d * 4));
+  CK(cudaMemcpy(dx, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(g, 0, (size_t)d * d * 4));
+  const float* slice = dx + (size_t)off * d;
+  auto xrow = [&](int64_t k) { return &hx[(((size_t)(k / seg_rows)) * n_tok + off + (k % seg_rows)) * d]; };
+  std::vector<int> rs;
+  if (host_ref) for (int r = 0; r < d; ++r) rs.push_back(r);
+  else for (int t = 0; t < 12; ++t) rs.push_back((int)(((int64_t)t * 2654435761ll + 17) % d));
+  std::vector<double> ref((size_t)d * d, 0.0);
+  for (int r : rs) {
+    double* o = &ref[(size_t)r * d];
+    for (int c = 0; c < d; ++c) o[c] = 0;
+    for (int64_t k = 0; k < rows; ++k) {
+      const float* xr = xrow(k);
+      const double a = xr[r];
+      for (int c = r; c < d; ++c) o[c] += a * (double)xr[c];
+    }
+  }
+  VK(vlm_tf32_split(slice, rows, d, d, nseg > 1 ? seg_rows : 0, (int64_t)n_tok * d, planes, nullptr));
+  VK(vlm_syrk_accum(planes, VLM_TF32X2, rows, d, d, g, d, nullptr));
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("SPLIT %-27s KERNEL FAILED: %s\n", name, cudaGetErrorString(e));
+    exit(97);
+  }
+  std::vector<float> out((size_t)d * d);
+  CK(cudaMemcpy(out.data(), g, out.size() * 4, cudaMemcpyDeviceToHost));
+  double num = 0, den = 0, max_abs = 0;
+  for (int r : rs)
+    for (int c = r; c < d; ++c) {
+      const double df = out[(size_t)r * d + c] - ref[(size_t)r * d + c];
+      num += df * df;
+      den += ref[(size_t)r * d + c] * ref[(size_t)r * d + c];
+      if (fabs(df) > max_abs) max_abs = fabs(df);
+    }
+  const double err = sqrt(num / den);
+  float ms_split = 0, ms_syrk = 0;
+  if (iters > 0) {
+    Timer t;
+    for (int i = 0; i < 2; ++i) VK(vlm_syrk_accum(planes, VLM_TF32X2, rows, d, d, g, d, nullptr));
+    t.start();
+    for (int i = 0; i < iters; ++i) VK(vlm_syrk_accum(planes, VLM_TF32X2, rows, d, d, g, d, nullptr));
+    ms_syrk = t.stop() / iters;
+    t.start();
+    for (int i = 0; i < iters; ++i) VK(vlm_tf32_split(slice, rows, d, d, nseg > 1 ? seg_rows : 0, (int64_t)n_tok * d, planes, nullptr));
+    ms_split = t.stop() / iters;
+  }
+  const double flops = (double)rows * d * (d + 1.0);
+  const bool ok = err <= tol && std::isfinite(err);
+  printf("SPLIT %-27s rows=%-6lld d=%-5d relF=%.3e maxabs=%.3e  split %.3f ms + syrk %.3f ms  %.1f TFLOP/s(sym, 1x count)  %s\n",
+         name, (long long)rows, d, err, max_abs, ms_split, ms_syrk, ms_syrk > 0 ? flops / (ms_syrk + ms_split) * 1e-9 : 0.0,
+         ok ? "OK" : "FAIL");
+  if (!ok) ++g_fail;
+  CK(cudaFree(dx));
+  CK(cudaFree(planes));
+  CK(cudaFree(g));
+}
+
 // Row-sliced activation: the view h[:, off:off+seg_rows] of an (nseg, n_tok, d) tensor, read in place
 // (vlm_syrk_accum_strided, and the same problem through vlm_syrk_accum_batch) against a host fp64 Gram of the
 // slice (host_ref) or the contiguous kernel on a packed copy of the slice.
@@ -559,6 +628,11 @@ int main(int argc, char** argv) {
     else syrk_case<__half>("case f16", VLM_F16, rows, d, mode, false, iters, 1e-4);
     return g_fail;
   }
+  if (argc >= 5 && !strcmp(argv[1], "split")) {  // selftest split <rows> <d> <iters> [positive]
+    syrk_split_case("case tf32x3", 1, atoi(argv[2]), 0, atoi(argv[2]), atoi(argv[3]), argc > 5 ? atoi(argv[5]) : 0, false,
+                    atoi(argv[4]), 2e-6);
+    return g_fail;
+  }
   if (argc >= 2 && !strcmp(argv[1], "pack")) {  // packed upper-triangle kernels only (for compute-sanitizer)
     for (int d : {1, 31, 33, 192, 768, 1000}) pack_case(d, d % 2 ? 3 : 0);
     return g_fail;
@@ -601,6 +675,15 @@ int main(int argc, char** argv) {
   syrk_case<__half>("f16 d=768 positive", VLM_F16, 1000, 768, 1, true, 0, 1e-5);
   syrk_case<__nv_bfloat16>("bf16 d=200 ragged", VLM_BF16, 77, 200, 1, true, 0, 1e-5);
   syrk_case<float>("f32 d=768 positive", VLM_F32, 2560, 768, 1, true, 0, 2e-3);
+
+  // split precision (3xTF32)
+  syrk_split_case("tf32x3 1 tile", 1, 64, 0, 64, 128, 0, true, 0, 2e-6);
+  syrk_split_case("tf32x3 d=768 ragged rows", 1, 1000, 0, 1000, 768, 0, true, 0, 2e-6);
+  syrk_split_case("tf32x3 d=800 positive", 1, 333, 0, 333, 800, 1, true, 0, 2e-6);
+  syrk_split_case("tf32x3 image slice", 4, 617, 40, 577, 768, 0, true, 0, 2e-6);
+  syrk_split_case("tf32x3 text d=3072", 1, 2560, 0, 2560, 3072, 1, false, 20, 2e-6);
+  syrk_split_case("tf32x3 image d=768", 1, 36928, 0, 36928, 768, 0, false, 20, 2e-6);
+  syrk_split_case("tf32x3 image d=3072", 1, 36928, 0, 36928, 3072, 1, false, 10, 4e-6);
 
   // row-sliced activations of the fused vision-language route: text rows [0, 40), image rows [40, 617)
   syrk_strided_case<float>("f32 text slice", VLM_F32, 8, 617, 0, 40, 768, true, 0, 2e-3);

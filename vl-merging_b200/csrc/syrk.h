@@ -37,14 +37,15 @@ struct PairSeg {
 };
 void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairSeg>* segs, std::vector<int>* off);
 
-// second generation: CTA pairs + TMA multicast + 3-D boxes (syrk_tc2.cu); needs whole 128-byte column groups
+// CTA-pair kernels (syrk_tc2.cu: cta_group::2 by default, the multicast pair kernel with VLM_SYRK_VARIANT=2);
+// need whole 128-byte column groups
 bool syrk_tc2_supported(int dtype, int d, int64_t ldx);
 // seg_rows > 0: X is rows/seg_rows row segments of seg_rows rows, seg_stride elements apart (0: contiguous rows)
 int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
                     float* g, int64_t ldg, cudaStream_t stream);
-// experimental (VLM_SYRK_VARIANT=4): one CTA per 256 x 256 super-tile, two M = 128 instruction streams sharing B
-int syrk_tc4_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
-                    float* g, int64_t ldg, cudaStream_t stream);
+// fp32 -> [2][rows][d] {hi, lo} TF32 planes (the VLM_TF32X2 operand of the pair kernel, syrk_2sm.cuh)
+int tf32_split_launch(const float* x, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride, float* out,
+                      cudaStream_t stream);
 // several independent problems (same dtype) in one grid; every problem must satisfy syrk_tc2_supported
 int syrk_tc2_batch_launch(const vlm_syrk_problem* probs, int n, int dtype, cudaStream_t stream);
 void build_syrk_pair_schedule_host(int64_t kc, int d, int nsm, std::vector<int32_t>* flat, std::vector<int>* off);

@@ -371,208 +371,13 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Fourth variant (VLM_SYRK_VARIANT=4, experimental): ONE CTA forms a whole 256 x 256 super-tile with two M = 128
-// instruction streams that share the B operand.  The CTA-pair kernel above is bound by what an SM can take in from L2
-// (69 B/clk: 48 KB per chunk for 128 x 256 outputs); here a chunk brings in 64 KB (A pair + B pair,
-// two TMA boxes of two blocks each) for 256 x 256 outputs — a third less per flop — so the loop becomes MMA-bound.
-// No cluster, no multicast.  The price: the two accumulators take all 512 TMEM columns, so a segment's epilogue is
-// not hidden behind the next segment's mainloop, and three 64 KB stages instead of four 48 KB ones.
-constexpr int kStages4 = 3;
-constexpr int kStageBytes4 = 4 * kBlockBytes;  // [B0][B1][A0][A1]
-constexpr int kSmemBytes4 = kStages4 * kStageBytes4 + 2 * kStagingBytes + 256 + 1024;
+}  // namespace
+}  // namespace vlm
 
-template <int ELEM_BYTES, int FMT>
-__global__ void __launch_bounds__(kThreads, 1)
-syrk_tc4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
-                const PairSeg* __restrict__ segs, const int* __restrict__ seg_off, int d, int cps, int l2_hints) {
-  using G = Geo<ELEM_BYTES>;
-  constexpr int kRows = G::BK;
-  constexpr int kBlk = kBlockBytes;
-  constexpr int kBox = G::BOX_BYTES;
-  constexpr int kNumMma = G::NUM_MMA;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stage_base = smem;
-  uint8_t* staging = smem + kStages4 * kStageBytes4;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kStages4;
-  uint64_t* tfull = bars + 2 * kStages4;
-  uint64_t* tempty = bars + 2 * kStages4 + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages4 + 2);
+#include "syrk_2sm.cuh"
 
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int seg_begin = seg_off[blockIdx.x];
-  const int seg_end = seg_off[blockIdx.x + 1];
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_x);
-    tma_prefetch_desc(&tm_g);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kStages4; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
-    }
-    mbar_init(tfull, 1);
-    mbar_init(tempty, 128);
-    fence_barrier_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0 && lane == 0) {
-    // ===== TMA producer: B pair (column blocks 2b, 2b+1) and, off the diagonal, A pair (2a, 2a+1) =====
-    int stage = 0;
-    uint32_t phase = 0;
-    const uint64_t pol_x = l2_policy(l2_hints & 3);
-    for (int s = seg_begin; s < seg_end; ++s) {
-      const PairSeg seg = segs[s];
-      const bool diag = seg.sa == seg.sb;
-      const int a_group = 2 * seg.sa * G::GB;
-      const int b_group = 2 * seg.sb * G::GB;
-      const uint32_t bytes = (diag ? 2u : 4u) * kBlk;
-      int xseg = cps > 0 ? seg.k0 / cps : 0;
-      int kin = seg.k0 - xseg * cps;
-      for (int k = seg.k0; k < seg.k1; ++k) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full[stage], bytes);
-        uint8_t* sb = stage_base + stage * kStageBytes4;
-        const int row = kin * kRows;
-        if (cps > 0) {
-          tma_load_4d(&tm_x, &full[stage], sb, 0, row, b_group, xseg, pol_x);
-          if (!diag) tma_load_4d(&tm_x, &full[stage], sb + 2 * kBlk, 0, row, a_group, xseg, pol_x);
-        } else {
-          tma_load_3d(&tm_x, &full[stage], sb, 0, row, b_group, pol_x);
-          if (!diag) tma_load_3d(&tm_x, &full[stage], sb + 2 * kBlk, 0, row, a_group, pol_x);
-        }
-        if (++kin == cps) {
-          kin = 0;
-          ++xseg;
-        }
-        if (++stage == kStages4) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer: whole warp walks the loop, one elected lane issues =====
-    int stage = 0;
-    uint32_t phase = 0, acc_phase = 0;
-    const uint32_t stage0 = smem_u32(stage_base);
-    constexpr uint32_t kDescHi = (uint32_t)((G::SBO_BYTES >> 4) & 0x3FFF) | (1u << 14) | ((uint32_t)G::LAYOUT_TYPE << 29);
-    constexpr uint32_t kDescLo = (uint32_t)((kBox >> 4) & 0x3FFF) << 16;
-    constexpr uint32_t idesc256 = make_idesc(FMT, 256);
-    constexpr uint32_t idesc128 = make_idesc(FMT, 128);
-    for (int s = seg_begin; s < seg_end; ++s) {
-      const PairSeg seg = segs[s];
-      const int sa_t = __shfl_sync(0xffffffffu, seg.sa, 0), sb_t = __shfl_sync(0xffffffffu, seg.sb, 0);
-      const int k0 = __shfl_sync(0xffffffffu, seg.k0, 0), k1 = __shfl_sync(0xffffffffu, seg.k1, 0);
-      const bool diag = sa_t == sb_t;
-      const uint32_t a_off = diag ? 0u : 2u * kBlk;   // A pair = B pair on a diagonal super-tile
-      mbar_wait(tempty, acc_phase ^ 1);
-      tc_fence_after();
-      for (int k = k0; k < k1; ++k) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        const uint32_t sb = stage0 + stage * kStageBytes4;
-        const uint32_t blo = ((sb & 0x3FFFFu) >> 4) | kDescLo;                 // B pair: N = 256
-        const uint32_t b1lo = (((sb + kBlk) & 0x3FFFFu) >> 4) | kDescLo;       // B block 1 alone: N = 128
-        const uint32_t a0lo = (((sb + a_off) & 0x3FFFFu) >> 4) | kDescLo;
-        const uint32_t a1lo = (((sb + a_off + kBlk) & 0x3FFFFu) >> 4) | kDescLo;
-        if (elect_one()) {
-          // rows 2a: blocks (2a, 2b), (2a, 2b+1) -> accumulator columns 0..255
-#pragma unroll
-          for (int kk = 0; kk < kNumMma; ++kk) {
-            const uint32_t st = kk * (G::KSTEP_BYTES >> 4);
-            umma<FMT>(tmem_base, ((uint64_t)kDescHi << 32) | (a0lo + st), ((uint64_t)kDescHi << 32) | (blo + st), idesc256,
-                      (k > k0 || kk > 0) ? 1u : 0u);
-          }
-          // rows 2a+1 -> accumulator columns 256..511; on the diagonal only block (2a+1, 2a+1): N = 128
-#pragma unroll
-          for (int kk = 0; kk < kNumMma; ++kk) {
-            const uint32_t st = kk * (G::KSTEP_BYTES >> 4);
-            if (diag)
-              umma<FMT>(tmem_base + 256, ((uint64_t)kDescHi << 32) | (a1lo + st), ((uint64_t)kDescHi << 32) | (b1lo + st),
-                        idesc128, (k > k0 || kk > 0) ? 1u : 0u);
-            else
-              umma<FMT>(tmem_base + 256, ((uint64_t)kDescHi << 32) | (a1lo + st), ((uint64_t)kDescHi << 32) | (blo + st),
-                        idesc256, (k > k0 || kk > 0) ? 1u : 0u);
-          }
-          tc_commit(&empty[stage]);
-        }
-        __syncwarp();
-        if (++stage == kStages4) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-      if (elect_one()) tc_commit(tfull);
-      __syncwarp();
-      acc_phase ^= 1;
-    }
-  } else if (warp >= 4) {
-    // ===== epilogue: 16 slabs of 128 rows x 32 columns (8 per accumulator half) =====
-    const int q = warp - 4;
-    const int epi_tid = threadIdx.x - 128;
-    const int row = q * 32 + lane;
-    uint32_t acc_phase = 0;
-    uint32_t slab_counter = 0;
-    const uint64_t pol_g = l2_policy((l2_hints >> 2) & 3);
-    for (int s = seg_begin; s < seg_end; ++s) {
-      const PairSeg seg = segs[s];
-      const bool diag = seg.sa == seg.sb;
-      mbar_wait(tfull, acc_phase);
-      tc_fence_after();
-      for (int sl = 0; sl < 16; ++sl) {
-        const int half = sl >> 3;                            // 0: rows of block 2a, 1: rows of block 2a+1
-        const int row0 = (2 * seg.sa + half) * 128;
-        // diagonal tile, second half: accumulator columns 256..383 hold block (2a+1, 2a+1)
-        const int col = (diag && half) ? (2 * seg.sb + 1) * 128 + (sl - 8) * 32 : 2 * seg.sb * 128 + (sl & 7) * 32;
-        if (row0 >= d || col >= d || (diag && half && sl >= 12)) continue;   // uniform over the 128 epilogue threads
-        uint8_t* buf = staging + (slab_counter & 1) * kStagingBytes;
-        if (epi_tid == 0) bulk_wait_group_read<1>();
-        named_bar_sync(1, 128);
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + sl * 32, v);
-        tmem_ld_wait();
-        const uint32_t rbase = smem_u32(buf) + row * 128;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint32_t addr = rbase + ((uint32_t)(c ^ (row & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * c]), "r"(v[4 * c + 1]),
-                       "r"(v[4 * c + 2]), "r"(v[4 * c + 3])
-                       : "memory");
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (epi_tid == 0) {
-          tma_reduce_add_2d_hint(&tm_g, buf, col, row0, pol_g);
-          bulk_commit_group();
-        }
-        ++slab_counter;
-      }
-      tc_fence_before();
-      mbar_arrive(tempty);
-      acc_phase ^= 1;
-    }
-    if (epi_tid == 0) bulk_wait_group<0>();
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
-}
-
+namespace vlm {
+namespace {
 struct DeviceSchedule2 {
   int nclusters = 0;
   PairSeg* d_segs = nullptr;
@@ -580,6 +385,9 @@ struct DeviceSchedule2 {
 };
 std::mutex g_mu2;
 std::map<std::tuple<int, int64_t, int, int, int>, DeviceSchedule2> g_sched2;
+// schedules evicted from the cache: freed at the NEXT eviction, after a device synchronisation, never while a
+// launch that was handed their pointers may still be pending (the lock is held from lookup to launch)
+std::vector<DeviceSchedule2> g_retired2;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -599,33 +407,40 @@ int ensure_encode() {
   return 0;
 }
 
-// X as a 3-D tensor {column in group, row, column group} (strides: row pitch, 128 bytes); G as a 2-D fp32 tensor
-// (seg_rows > 0: 4-D, {column in group, row in segment, column group, segment})
-// box_blocks: 128-column blocks fetched by one box (1: the CTA-pair kernel, 2: the single-CTA 256 x 256 kernel)
+inline int elem_bytes(int dtype) { return (dtype == VLM_F32 || dtype == VLM_TF32X2) ? 4 : 2; }
+// rows of X per pipeline stage = schedule chunk
+inline int chunk_rows(int dtype) { return dtype == VLM_TF32X2 ? 16 : 128 / elem_bytes(dtype); }
+
+// X as a 3-D tensor {column in group, row, column group} (strides: row pitch, 128 bytes); G as a 2-D fp32 tensor.
+// seg_rows > 0: 4-D, {column in group, row in segment, column group, segment}.
+// VLM_TF32X2: 4-D, {column in group, row, column group, plane}, planes rows * ldx elements apart, and one box
+// fetches both planes of a 128-column block for 16 rows.
 int encode_maps(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
-                float* g, int64_t ldg, CUtensorMap* tm_x, CUtensorMap* tm_g, int box_blocks = 1) {
-  const int elem = (dtype == VLM_F32) ? 4 : 2;
-  const int bk = 128 / elem, gc = 128 / elem;
+                float* g, int64_t ldg, CUtensorMap* tm_x, CUtensorMap* tm_g) {
+  const int elem = elem_bytes(dtype);
+  const int bk = chunk_rows(dtype), gc = 128 / elem;
   {
     // fp32 activations are described to TMA as TFLOAT32: the copy engine then ROUNDS each value to TF32 on its
     // way into shared memory.  With the plain FLOAT32 element type the tensor core truncates the low 13
     // mantissa bits of both operands instead, a systematic -6.8e-4 relative bias on every Gram (measured on the
     // B200, 36928 x 3072: rel. Frobenius error 7.6e-4 truncated vs 2.5e-5 rounded, same speed).
-    const CUtensorMapDataType dt = dtype == VLM_F32    ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
+    // (The planes of VLM_TF32X2 hold TF32 values already: the conversion is then the identity.)
+    const CUtensorMapDataType dt = elem == 4             ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
                                    : dtype == VLM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                                        : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    const bool segmented = seg_rows > 0;
+    const bool split = dtype == VLM_TF32X2;
+    const bool segmented = !split && seg_rows > 0;
+    const int rank = (split || segmented) ? 4 : 3;
     cuuint64_t gdim[4] = {(cuuint64_t)gc, (cuuint64_t)(segmented ? seg_rows : rows), (cuuint64_t)(d / gc),
-                          (cuuint64_t)(segmented ? rows / seg_rows : 1)};
-    cuuint64_t gstr[3] = {(cuuint64_t)ldx * elem, 128, (cuuint64_t)seg_stride * elem};
-    cuuint32_t box[4] = {(cuuint32_t)gc, (cuuint32_t)bk, (cuuint32_t)(elem * box_blocks) /* groups per 128-column block */, 1};
+                          (cuuint64_t)(split ? 2 : segmented ? rows / seg_rows : 1)};
+    cuuint64_t gstr[3] = {(cuuint64_t)ldx * elem, 128, (cuuint64_t)(split ? rows * ldx : seg_stride) * elem};
+    cuuint32_t box[4] = {(cuuint32_t)gc, (cuuint32_t)bk, (cuuint32_t)elem /* groups per 128-column block */,
+                         (cuuint32_t)(split ? 2 : 1)};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUtensorMapSwizzle swz = elem == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
-    CUresult r = g_encode2(tm_x, dt, segmented ? 4 : 3, const_cast<void*>(x), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    VLM_REQUIRE(r == CUDA_SUCCESS, VLM_ERR_DRIVER, "cuTensorMapEncodeTiled(X, %d-D) failed: CUresult %d",
-                segmented ? 4 : 3, (int)r);
+    CUresult r = g_encode2(tm_x, dt, rank, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VLM_REQUIRE(r == CUDA_SUCCESS, VLM_ERR_DRIVER, "cuTensorMapEncodeTiled(X, %d-D) failed: CUresult %d", rank, (int)r);
   }
   {
     cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)d};
@@ -666,19 +481,32 @@ int l2_hints() {
   return v;
 }
 
-template <int ELEM_BYTES, int FMT>
-int launch_kernel2(int dev, const DeviceSchedule2& sched, const CUtensorMap& tm_x, const CUtensorMap& tm_g, int d,
-                   int cps, cudaStream_t stream) {
-  static std::atomic<bool> attr_done[64];
-  auto kernel = syrk_tc2_kernel<ELEM_BYTES, FMT, false>;
-  if (dev >= 64 || !attr_done[dev].load(std::memory_order_acquire)) {
-    VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    if (dev < 64) attr_done[dev].store(true, std::memory_order_release);
+// Which pair kernel: 3 = one cta_group::2 instruction stream per pair (syrk_2sm.cuh, the default), 2 = two
+// cta_group::1 streams with TMA multicast (kept selectable with VLM_SYRK_VARIANT=2 for A/B measurements).
+// VLM_TF32X2 exists only in the 2-SM kernel.
+int pair_variant(int dtype) {
+  static const int v = [] {
+    const char* e = getenv("VLM_SYRK_VARIANT");
+    return (e && atoi(e) == 2) ? 2 : 3;
+  }();
+  return dtype == VLM_TF32X2 ? 3 : v;
+}
+
+typedef void (*PairKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap*, const void*, const int*, int, int,
+                           int);
+template <bool BATCH>
+PairKernel pick_kernel(int dtype, int variant, int* smem) {
+  if (variant == 2) {
+    *smem = kSmemBytes;
+    if (dtype == VLM_F32) return syrk_tc2_kernel<4, 2, BATCH>;
+    if (dtype == VLM_BF16) return syrk_tc2_kernel<2, 1, BATCH>;
+    return syrk_tc2_kernel<2, 0, BATCH>;
   }
-  kernel<<<2 * sched.nclusters, kThreads, kSmemBytes, stream>>>(tm_x, tm_g, nullptr, sched.d_segs, sched.d_off, d, cps, l2_hints());
-  VLM_CUDA(cudaGetLastError());
-  count_launch();
-  return 0;
+  *smem = k2SmemBytes;
+  if (dtype == VLM_TF32X2) return syrk_2sm_kernel<4, 2, BATCH, true>;
+  if (dtype == VLM_F32) return syrk_2sm_kernel<4, 2, BATCH, false>;
+  if (dtype == VLM_BF16) return syrk_2sm_kernel<2, 1, BATCH, false>;
+  return syrk_2sm_kernel<2, 0, BATCH, false>;
 }
 
 }  // namespace
@@ -807,8 +635,7 @@ void build_syrk_pair_schedule_host(int64_t kc, int d, int nsm, std::vector<int32
 }
 
 bool syrk_tc2_supported(int dtype, int d, int64_t ldx) {
-  const int elem = (dtype == VLM_F32) ? 4 : 2;
-  return d % (128 / elem) == 0 && ldx >= d;  // whole 128-byte column groups (the 3-D tensor map needs them)
+  return d % (128 / elem_bytes(dtype)) == 0 && ldx >= d;  // whole 128-byte column groups (the 3-D tensor map needs them)
 }
 
 // chunks per row segment (0 = contiguous) and in total
@@ -824,10 +651,10 @@ static inline void seg_chunks(int64_t rows, int64_t seg_rows, int bk, int64_t* c
 
 int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
                     float* g, int64_t ldg, cudaStream_t stream) {
-  const int elem = (dtype == VLM_F32) ? 4 : 2;
-  const int bk = 128 / elem;  // rows per pipeline stage = schedule chunk
+  const int elem = elem_bytes(dtype);
+  const int bk = chunk_rows(dtype);
   if (int rc = check_alignment(x, elem, rows, ldx, g, ldg)) return rc;
-  if (seg_rows >= rows) seg_rows = 0;  // one segment: plain rows
+  if (seg_rows >= rows || dtype == VLM_TF32X2) seg_rows = 0;  // one segment: plain rows
   int dev = 0, nsm = 0;
   VLM_CUDA(cudaGetDevice(&dev));
   if (int rc = device_sm_count(&nsm)) return rc;
@@ -835,94 +662,63 @@ int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, 
   int64_t cps, kc;
   seg_chunks(rows, seg_rows, bk, &cps, &kc);
   VLM_REQUIRE(kc < (int64_t)1 << 30, VLM_ERR_INVALID_ARG, "vlm_syrk_accum: too many row chunks");
-  DeviceSchedule2 sched;
-  {
-    std::lock_guard<std::mutex> lk(g_mu2);
-    auto key = std::make_tuple(dev, kc, d, bk, nsm);
-    auto it = g_sched2.find(key);
-    if (it == g_sched2.end()) {
-      if (g_sched2.size() >= 512) {  // ragged workloads (a new row count every call): start over, do not grow forever
-        VLM_CUDA(cudaDeviceSynchronize());  // a launch in flight may still read an old schedule
-        for (auto& kv : g_sched2) {
-          cudaFree(kv.second.d_segs);
-          cudaFree(kv.second.d_off);
-        }
-        g_sched2.clear();
-      }
-      std::vector<PairSeg> segs;
-      std::vector<int> off;
-      build_pair_schedule(kc, d, nsm / 2, &segs, &off);
-      DeviceSchedule2 ds;
-      ds.nclusters = (int)off.size() - 1;
-      VLM_CUDA(cudaMalloc(&ds.d_segs, std::max<size_t>(1, segs.size()) * sizeof(PairSeg)));
-      VLM_CUDA(cudaMalloc(&ds.d_off, off.size() * sizeof(int)));
-      VLM_CUDA(cudaMemcpyAsync(ds.d_segs, segs.data(), segs.size() * sizeof(PairSeg), cudaMemcpyHostToDevice, stream));
-      VLM_CUDA(cudaMemcpyAsync(ds.d_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
-      VLM_CUDA(cudaStreamSynchronize(stream));
-      it = g_sched2.emplace(key, ds).first;
-    }
-    sched = it->second;
-  }
-
   CUtensorMap tm_x, tm_g;
   if (int rc = encode_maps(x, dtype, rows, d, ldx, seg_rows, seg_stride, g, ldg, &tm_x, &tm_g)) return rc;
-  if (dtype == VLM_F32) return launch_kernel2<4, 2>(dev, sched, tm_x, tm_g, d, (int)cps, stream);
-  if (dtype == VLM_BF16) return launch_kernel2<2, 1>(dev, sched, tm_x, tm_g, d, (int)cps, stream);
-  return launch_kernel2<2, 0>(dev, sched, tm_x, tm_g, d, (int)cps, stream);
+  int smem = 0;
+  PairKernel kernel = pick_kernel<false>(dtype, pair_variant(dtype), &smem);
+
+  // lookup and launch under one lock: an eviction by another host thread cannot free a schedule between the two
+  std::lock_guard<std::mutex> lk(g_mu2);
+  auto key = std::make_tuple(dev, kc, d, bk, nsm);
+  auto it = g_sched2.find(key);
+  if (it == g_sched2.end()) {
+    if (g_sched2.size() >= 512) {  // ragged workloads (a new row count every call): start over, do not grow forever
+      VLM_CUDA(cudaDeviceSynchronize());  // launches that read the schedules retired LAST time have finished
+      for (auto& ds : g_retired2) {
+        cudaFree(ds.d_segs);
+        cudaFree(ds.d_off);
+      }
+      g_retired2.clear();
+      for (auto& kv : g_sched2) g_retired2.push_back(kv.second);
+      g_sched2.clear();
+    }
+    std::vector<PairSeg> segs;
+    std::vector<int> off;
+    build_pair_schedule(kc, d, nsm / 2, &segs, &off);
+    DeviceSchedule2 ds;
+    ds.nclusters = (int)off.size() - 1;
+    VLM_CUDA(cudaMalloc(&ds.d_segs, std::max<size_t>(1, segs.size()) * sizeof(PairSeg)));
+    VLM_CUDA(cudaMalloc(&ds.d_off, off.size() * sizeof(int)));
+    VLM_CUDA(cudaMemcpyAsync(ds.d_segs, segs.data(), segs.size() * sizeof(PairSeg), cudaMemcpyHostToDevice, stream));
+    VLM_CUDA(cudaMemcpyAsync(ds.d_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    VLM_CUDA(cudaStreamSynchronize(stream));
+    it = g_sched2.emplace(key, ds).first;
+  }
+  const DeviceSchedule2& sched = it->second;
+  VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kernel<<<2 * sched.nclusters, kThreads, smem, stream>>>(tm_x, tm_g, nullptr, sched.d_segs, sched.d_off, d, (int)cps,
+                                                          l2_hints());
+  VLM_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
 }
 
-// Experimental single-CTA 256 x 256 variant (syrk_tc4_kernel): same contract as syrk_tc2_launch.
-int syrk_tc4_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
-                    float* g, int64_t ldg, cudaStream_t stream) {
-  const int elem = (dtype == VLM_F32) ? 4 : 2;
-  const int bk = 128 / elem;
-  if (int rc = check_alignment(x, elem, rows, ldx, g, ldg)) return rc;
-  if (seg_rows >= rows) seg_rows = 0;
-  int dev = 0, nsm = 0;
-  VLM_CUDA(cudaGetDevice(&dev));
+int tf32_split_launch(const float* x, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride, float* out,
+                      cudaStream_t stream) {
+  int nsm = 0;
   if (int rc = device_sm_count(&nsm)) return rc;
-  if (int rc = ensure_encode()) return rc;
-  int64_t cps, kc;
-  seg_chunks(rows, seg_rows, bk, &cps, &kc);
-  VLM_REQUIRE(kc < (int64_t)1 << 30, VLM_ERR_INVALID_ARG, "vlm_syrk_accum: too many row chunks");
-  DeviceSchedule2 sched;
-  {
-    std::lock_guard<std::mutex> lk(g_mu2);
-    auto key = std::make_tuple(dev, kc, d, bk, -nsm);   // negative: one CTA per super-tile share (nsm of them)
-    auto it = g_sched2.find(key);
-    if (it == g_sched2.end()) {
-      std::vector<PairSeg> segs;
-      std::vector<int> off;
-      build_pair_schedule(kc, d, nsm, &segs, &off);
-      DeviceSchedule2 ds;
-      ds.nclusters = (int)off.size() - 1;
-      VLM_CUDA(cudaMalloc(&ds.d_segs, std::max<size_t>(1, segs.size()) * sizeof(PairSeg)));
-      VLM_CUDA(cudaMalloc(&ds.d_off, off.size() * sizeof(int)));
-      VLM_CUDA(cudaMemcpyAsync(ds.d_segs, segs.data(), segs.size() * sizeof(PairSeg), cudaMemcpyHostToDevice, stream));
-      VLM_CUDA(cudaMemcpyAsync(ds.d_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
-      VLM_CUDA(cudaStreamSynchronize(stream));
-      it = g_sched2.emplace(key, ds).first;
-    }
-    sched = it->second;
-  }
-  CUtensorMap tm_x, tm_g;
-  if (int rc = encode_maps(x, dtype, rows, d, ldx, seg_rows, seg_stride, g, ldg, &tm_x, &tm_g, 2)) return rc;
-  auto launch = [&](auto kernel) -> int {
-    VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes4));
-    kernel<<<sched.nclusters, kThreads, kSmemBytes4, stream>>>(tm_x, tm_g, sched.d_segs, sched.d_off, d, (int)cps,
-                                                               l2_hints());
-    VLM_CUDA(cudaGetLastError());
-    count_launch();
-    return 0;
-  };
-  if (dtype == VLM_F32) return launch(syrk_tc4_kernel<4, 2>);
-  if (dtype == VLM_BF16) return launch(syrk_tc4_kernel<2, 1>);
-  return launch(syrk_tc4_kernel<2, 0>);
+  if (seg_rows >= rows) seg_rows = 0;
+  const int64_t n4 = rows * (d / 4);
+  const int64_t blocks = std::min<int64_t>((n4 + 255) / 256, (int64_t)nsm * 8);
+  tf32_split_kernel<<<(unsigned)std::max<int64_t>(1, blocks), 256, 0, stream>>>(x, rows, d, ldx, seg_rows, seg_stride, out);
+  VLM_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
 }
 
 int syrk_tc2_batch_launch(const vlm_syrk_problem* probs, int n, int dtype, cudaStream_t stream) {
-  const int elem = (dtype == VLM_F32) ? 4 : 2;
-  const int bk = 128 / elem;
+  const int elem = elem_bytes(dtype);
+  const int bk = chunk_rows(dtype);
   int dev = 0, nsm = 0;
   VLM_CUDA(cudaGetDevice(&dev));
   if (int rc = device_sm_count(&nsm)) return rc;
@@ -942,7 +738,7 @@ int syrk_tc2_batch_launch(const vlm_syrk_problem* probs, int n, int dtype, cudaS
   for (int p = 0; p < n; ++p) {
     const vlm_syrk_problem& q = probs[p];
     if (int rc = check_alignment(q.x, elem, q.rows, q.ldx, q.g, q.ldg)) return rc;
-    const int64_t seg_rows = (q.seg_rows > 0 && q.seg_rows < q.rows) ? q.seg_rows : 0;
+    const int64_t seg_rows = (dtype != VLM_TF32X2 && q.seg_rows > 0 && q.seg_rows < q.rows) ? q.seg_rows : 0;
     if (int rc = encode_maps(q.x, dtype, q.rows, q.d, q.ldx, seg_rows, q.seg_stride, q.g, q.ldg, &maps[2 * p],
                              &maps[2 * p + 1]))
       return rc;
@@ -1007,18 +803,15 @@ int syrk_tc2_batch_launch(const vlm_syrk_problem* probs, int n, int dtype, cudaS
   }
   // pageable source: staged before the call returns; ordered on `stream` before the kernel below
   VLM_CUDA(cudaMemcpyAsync(dptr, host.data(), total, cudaMemcpyHostToDevice, stream));
-  auto launch = [&](auto kernel) -> int {
-    VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    kernel<<<2 * ncl, kThreads, kSmemBytes, stream>>>(maps[0], maps[1], reinterpret_cast<const CUtensorMap*>(dptr),
-                                                        dptr + maps_bytes + off_bytes,
-                                                        reinterpret_cast<const int*>(dptr + maps_bytes), 0, 0, l2_hints());
-    VLM_CUDA(cudaGetLastError());
-    count_launch();
-    return 0;
-  };
-  if (dtype == VLM_F32) return launch(syrk_tc2_kernel<4, 2, true>);
-  if (dtype == VLM_BF16) return launch(syrk_tc2_kernel<2, 1, true>);
-  return launch(syrk_tc2_kernel<2, 0, true>);
+  int smem = 0;
+  PairKernel kernel = pick_kernel<true>(dtype, pair_variant(dtype), &smem);
+  VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kernel<<<2 * ncl, kThreads, smem, stream>>>(maps[0], maps[1], reinterpret_cast<const CUtensorMap*>(dptr),
+                                              dptr + maps_bytes + off_bytes,
+                                              reinterpret_cast<const int*>(dptr + maps_bytes), 0, 0, l2_hints());
+  VLM_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
 }
 
 }  // namespace vlm

@@ -84,8 +84,14 @@ class GramCache:
     """
 
     def __init__(self, device=None, use_simt=False, defer_bytes=0, max_pending=256, max_pending_bytes=1 << 30,
-                 side_stream=False):
-        """defer_bytes > 0: an activation of at most that many bytes is not launched on its own (the Gram of a
+                 side_stream=False, precision="tf32"):
+        """precision: how fp32 activations reach the tensor cores.  "tf32" (default): one TF32 pass, operands rounded
+        by TMA — Gram within ~3e-5 of the reference's fp64 Gram (cache_gram_matrices.py:251-252), inside the 1e-3
+        tolerance, but its 2^-11 operand rounding noise is amplified by the inverse in regmean
+        (vilt_module.py:432-434).  "tf32x3": RegMean-grade Grams — every fp32 activation is split into
+        {hi, lo} TF32 planes (vlm_tf32_split) and the kernel forms hi'hi + hi'lo + lo'hi, ~3x the tensor work;
+        bf16 / fp16 activations are exact on the tensor core either way.
+        defer_bytes > 0: an activation of at most that many bytes is not launched on its own (the Gram of a
         40-token text batch is launch-bound: ~7 us of fixed cost for ~2 us of tensor-core work, and a 768-wide
         image Gram exposes its prologue and final epilogue); the hook keeps a REFERENCE to it (no copy) and
         flush() issues everything pending as one grouped launch (vlm_syrk_accum_batch), in which one problem's
@@ -106,6 +112,10 @@ class GramCache:
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self._lib = _lib.lib()
+        if precision not in ("tf32", "tf32x3"):
+            raise ValueError(f"precision must be 'tf32' or 'tf32x3' (got {precision!r})")
+        self.precision = precision
+        self._planes = None    # scratch for the {hi, lo} planes of the split mode (grown on demand, reused in stream order)
         self._fn = self._lib.vlm_syrk_accum_simt if use_simt else self._lib.vlm_syrk_accum
         self.buffers = {}       # name -> fp32 [d, d] (upper triangle authoritative until finalize())
         self._arenas = []      # flat fp32 arenas the registered buffers are views of
@@ -154,6 +164,8 @@ class GramCache:
             rows, ldx, keep = x2.shape[0], (x2.stride(0) if x2.shape[0] > 1 else d), x2
         ptr = keep.data_ptr()
         simt = self._fn is self._lib.vlm_syrk_accum_simt or (ptr % 16) or ((ldx * elem) % 16)
+        if self.precision == "tf32x3" and keep.dtype == torch.float32 and d % 32:
+            simt = True                  # widths the split kernel does not take: CUDA cores, exact fp32 products
         if simt and seg_rows:
             keep = x.contiguous()        # the CUDA-core kernel takes plain rows only
             ptr, ldx, seg_rows, seg_stride = keep.data_ptr(), d, 0, 0
@@ -174,12 +186,32 @@ class GramCache:
                 self.flush()
             return
         stream = self._launch_stream(keep)
-        if seg_rows:
+        if self._split_ok(code, simt, d):
+            planes = self._plane_scratch(2 * rows * d)
+            _lib.check(self._lib.vlm_tf32_split(ptr, rows, d, ldx, seg_rows, seg_stride, planes.data_ptr(), stream))
+            _lib.check(self._lib.vlm_syrk_accum(planes.data_ptr(), _lib.VLM_TF32X2, rows, d, d, g.data_ptr(),
+                                                g.stride(0), stream))
+        elif seg_rows:
             _lib.check(self._lib.vlm_syrk_accum_strided(ptr, code, rows, d, ldx, seg_rows, seg_stride, g.data_ptr(),
                                                         g.stride(0), stream))
         else:
             fn = self._lib.vlm_syrk_accum_simt if simt else self._fn
             _lib.check(fn(ptr, code, rows, d, ldx, g.data_ptr(), g.stride(0), stream))
+
+    def _split_ok(self, code, simt, d):
+        return self.precision == "tf32x3" and code == _lib.VLM_F32 and not simt and d % 32 == 0
+
+    def _plane_scratch(self, numel):
+        """fp32 scratch of at least `numel` elements for the {hi, lo} planes.  One buffer, reused by every launch:
+        all launches of a cache go to one stream (the current or the side stream), which orders the reuse."""
+        if self._planes is None or self._planes.numel() < numel:
+            if self._planes is not None and self._side is not None:
+                self._planes.record_stream(self._side)
+            self._planes = None
+            self._planes = torch.empty(int(numel), dtype=torch.float32, device=self.device)
+            if self._side is not None:
+                self._planes.record_stream(self._side)
+        return self._planes
 
     def _launch_stream(self, keep=None):
         """Raw handle of the stream a SYRK launch goes to.  Side-stream mode: the side stream, made to wait for
@@ -213,10 +245,21 @@ class GramCache:
         for code in sorted({p[0] for p in pending}):
             group = [p for p in pending if p[0] == code]
             probs = (_lib.SyrkProblem * len(group))()
-            for q, (_, _keep, g, ptr, rows, d, ldx, seg_rows, seg_stride) in zip(probs, group):
-                q.x, q.rows, q.ldx, q.g, q.ldg, q.d = ptr, rows, ldx, g.data_ptr(), g.stride(0), d
-                q.seg_rows, q.seg_stride = seg_rows, seg_stride
-            _lib.check(self._lib.vlm_syrk_accum_batch(probs, len(group), code, stream))
+            split = [self._split_ok(code, False, p[5]) for p in group]
+            if any(split):      # split mode: the planes of every problem of the group, back to back in the scratch
+                planes = self._plane_scratch(sum(2 * p[4] * p[5] for p, s in zip(group, split) if s))
+                off = 0
+            for q, (_, _keep, g, ptr, rows, d, ldx, seg_rows, seg_stride), sp in zip(probs, group, split):
+                if sp:
+                    dst = planes.data_ptr() + off * 4
+                    _lib.check(self._lib.vlm_tf32_split(ptr, rows, d, ldx, seg_rows, seg_stride, dst, stream))
+                    off += 2 * rows * d
+                    q.x, q.rows, q.ldx, q.g, q.ldg, q.d, q.seg_rows, q.seg_stride = dst, rows, d, g.data_ptr(), g.stride(0), d, 0, 0
+                else:
+                    q.x, q.rows, q.ldx, q.g, q.ldg, q.d = ptr, rows, ldx, g.data_ptr(), g.stride(0), d
+                    q.seg_rows, q.seg_stride = seg_rows, seg_stride
+            _lib.check(self._lib.vlm_syrk_accum_batch(probs, len(group), _lib.VLM_TF32X2 if any(split) else code,
+                                                      stream))
         self._join()
         # `pending` (and with it the activations) is released here: the launches are already ordered on the stream
 
