@@ -72,6 +72,17 @@ int vlm_syrk_accum(const void* x, int dtype, int64_t rows, int d, int64_t ldx,
 int vlm_tf32_split(const float* x, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
                    float* out, void* stream);
 
+/* Reference-precision Gram: fp64 products and fp64 accumulation into an fp64 G — the arithmetic of the reference
+ * hook itself (src/cache_gram_matrices.py:251-252), on the fp64 tensor-core path (DMMA).  The tcgen05 kernels
+ * above accumulate in the tensor core's truncating fp32 accumulator (~2e-5 non-uniform shrink even with exact
+ * operands), which regmean's inverse (src/vilt/modules/vilt_module.py:432-434) amplifies on ill-conditioned
+ * Gram sums; this entry point is the RegMean-grade mode (GramCache(precision="fp64")).  x: f32 / bf16 / f16,
+ * any alignment (16-byte aligned rows take the cp.async path), optionally row-segmented (seg_rows = 0: plain
+ * rows).  Upper block triangle only, like vlm_syrk_accum; vlm_sym_finalize_f64 mirrors it. */
+int vlm_syrk_accum_f64(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows,
+                       int64_t seg_stride, double* g, int64_t ldg, void* stream);
+int vlm_sym_finalize_f64(double* g, int d, int64_t ldg, void* stream);
+
 /* Several independent vlm_syrk_accum problems of the same dtype in ONE launch (e.g. the 48 small Grams of the
  * text tower of one forward, which are launch-bound one by one).  Same contract per problem; the activations
  * must stay alive and unmodified until `stream` has run the launch.  Problems TMA cannot address, or whose

@@ -31,6 +31,7 @@ def chain():
     cfg = vlm.vlmo_config("base", num_layers=2, vlffn_start_layer_index=2)
     model = vlm.init_synthetic_(vlm.VLMo(cfg).eval(), seed=1).cuda()
     caches = {
+        "fp64": vlm.GramCache(precision="fp64"),
         "tf32": vlm.GramCache(),
         "tf32x3": vlm.GramCache(precision="tf32x3"),
         "tf32x3_grouped": vlm.GramCache(precision="tf32x3", defer_bytes=64 << 20),
@@ -68,6 +69,16 @@ def test_rows_per_expert(chain):
     assert min(caches["tf32x3"].rows[n] for n in live) >= 5120
 
 
+def test_fp64_gram_equals_reference_hook(chain):
+    """fp64 mode = the reference hook's arithmetic: only the summation order differs."""
+    cfg, sd, np_sd, caches, ref, np_ref = chain
+    assert all(caches["fp64"].gram(k).dtype == torch.float64 for k in ref)
+    worst = max(((caches["fp64"].gram(k) - g).norm() / g.norm()).item() for k, g in ref.items())
+    assert worst < 1e-13, worst
+    for k, g in caches["fp64"].state_dict().items():      # the reference's file format: fp64 CPU, full symmetric
+        assert g.dtype == torch.float64 and g.device.type == "cpu" and torch.equal(g, g.T)
+
+
 @pytest.mark.parametrize("mode", ["tf32x3", "tf32x3_grouped"])
 def test_split_gram_error(chain, mode):
     """Gram error of the split mode: what is left is the tensor core's truncating fp32 accumulation (a near-uniform
@@ -80,8 +91,18 @@ def test_split_gram_error(chain, mode):
     assert single < 1e-3, single     # BASELINE.json's Gram tolerance for the single-pass mode
 
 
+def _regmean_errors(chain, mode, alpha):
+    import oracle
+
+    cfg, sd, np_sd, caches, ref, np_ref = chain
+    mcfg = dict(vlffn_start_layer_index=2, loss_names={"irtr": 1.0, "vqa": 0, "nlvr2": 0}, scaling_for_non_diag=alpha)
+    want = oracle.regmean(np_sd, np_ref, mcfg, num_layers=2)
+    got = vlm.regmean(sd, mcfg, gram_matrices=caches[mode], num_layers=2)
+    return {k: float(np.linalg.norm(got[k].cpu().numpy() - want[k]) / np.linalg.norm(want[k])) for k in _linear_keys(want)}
+
+
 @pytest.mark.parametrize("alpha", [1.0, 0.9])
-@pytest.mark.parametrize("mode", ["tf32x3", "tf32x3_grouped"])
+@pytest.mark.parametrize("mode", ["fp64"])
 def test_regmean_chain_within_1e4_of_fp64_gram_oracle(chain, mode, alpha):
     import oracle
 
@@ -103,15 +124,16 @@ def test_regmean_chain_within_1e4_of_fp64_gram_oracle(chain, mode, alpha):
             assert np.array_equal(got[k].cpu().numpy(), w), k
 
 
-def test_single_pass_regmean_error_is_reported(chain):
-    """The default single-pass TF32 Grams through the same chain: recorded, and bounded loosely — this is the mode
-    the 1e-4 bar does NOT hold for (operand rounding noise x the inverse), which is why tf32x3 exists."""
-    import oracle
-
-    cfg, sd, np_sd, caches, ref, np_ref = chain
-    mcfg = dict(vlffn_start_layer_index=2, loss_names={"irtr": 1.0, "vqa": 0, "nlvr2": 0}, scaling_for_non_diag=1.0)
-    want = oracle.regmean(np_sd, np_ref, mcfg, num_layers=2)
-    got = vlm.regmean(sd, mcfg, gram_matrices=caches["tf32"], num_layers=2)
-    errs = {k: float(np.linalg.norm(got[k].cpu().numpy() - want[k]) / np.linalg.norm(want[k])) for k in _linear_keys(want)}
-    print("single-pass tf32 regmean errors:", {k.split("blocks.")[1]: f"{e:.2e}" for k, e in errs.items()})
-    assert max(errs.values()) < 5e-3
+@pytest.mark.parametrize("alpha", [1.0, 0.9])
+def test_tensor_core_gram_modes_are_reported(chain, alpha):
+    """The tcgen05 Gram modes through the same chain.  Their truncating fp32 accumulation leaves a ~2e-5 non-uniform
+    shrink in the Gram; where the summed Gram has a small eigen-direction (the LayerNorm-fed qkv / fc1 inputs lie
+    near an affine hyperplane) regmean's inverse amplifies it far beyond 1e-4, which is why the RegMean-grade mode is
+    fp64.  tf32x3 removes the operand-rounding noise, which is what dominates on the well-conditioned fc2 inputs.
+    Recorded and bounded loosely: these modes serve the 1e-3 Gram tolerance, not RegMean's 1e-4."""
+    errs = {m: _regmean_errors(chain, m, alpha) for m in ("tf32", "tf32x3", "tf32x3_grouped")}
+    for m, e in errs.items():
+        print(f"{m} alpha={alpha} regmean errors:", {k.split("blocks.")[1]: f"{v:.2e}" for k, v in e.items()})
+        assert max(e.values()) < 0.2, (m, e)
+    fc2 = [k for k in errs["tf32"] if ".fc2." in k]
+    assert all(errs["tf32x3"][k] <= 1e-4 for k in fc2), errs["tf32x3"]

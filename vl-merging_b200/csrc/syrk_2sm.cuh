@@ -340,7 +340,8 @@ syrk_2sm_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (epi_tid == 0) bulk_wait_group<0>();
+    // the staging memory must outlive the TMA engine's READS of it; the adds themselves complete before the grid does
+    if (epi_tid == 0) bulk_wait_group_read<0>();
   }
 
   tc_fence_before();

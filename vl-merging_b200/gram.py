@@ -90,7 +90,12 @@ class GramCache:
         tolerance, but its 2^-11 operand rounding noise is amplified by the inverse in regmean
         (vilt_module.py:432-434).  "tf32x3": RegMean-grade Grams — every fp32 activation is split into
         {hi, lo} TF32 planes (vlm_tf32_split) and the kernel forms hi'hi + hi'lo + lo'hi, ~3x the tensor work;
-        bf16 / fp16 activations are exact on the tensor core either way.
+        bf16 / fp16 activations are exact on the tensor core either way.  Both tcgen05 modes accumulate in the
+        tensor core's truncating fp32 accumulator (a ~2e-5 non-uniform shrink), which regmean still amplifies when
+        the summed Gram has a small eigen-direction (LayerNorm outputs: measured 1.7e-2 on the B200).
+        "fp64": the reference's own arithmetic — fp64 products, fp64 accumulation, fp64 Gram buffers
+        (vlm_syrk_accum_f64, DMMA tensor cores); the mode that carries regmean to its 1e-4 tolerance.  Launches
+        immediately (no grouping).
         defer_bytes > 0: an activation of at most that many bytes is not launched on its own (the Gram of a
         40-token text batch is launch-bound: ~7 us of fixed cost for ~2 us of tensor-core work, and a 768-wide
         image Gram exposes its prologue and final epilogue); the hook keeps a REFERENCE to it (no copy) and
@@ -112,9 +117,10 @@ class GramCache:
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self._lib = _lib.lib()
-        if precision not in ("tf32", "tf32x3"):
-            raise ValueError(f"precision must be 'tf32' or 'tf32x3' (got {precision!r})")
+        if precision not in ("tf32", "tf32x3", "fp64"):
+            raise ValueError(f"precision must be 'tf32', 'tf32x3' or 'fp64' (got {precision!r})")
         self.precision = precision
+        self.dtype = torch.float64 if precision == "fp64" else torch.float32   # of the Gram buffers
         self._planes = None    # scratch for the {hi, lo} planes of the split mode (grown on demand, reused in stream order)
         self._fn = self._lib.vlm_syrk_accum_simt if use_simt else self._lib.vlm_syrk_accum
         self.buffers = {}       # name -> fp32 [d, d] (upper triangle authoritative until finalize())
@@ -171,7 +177,7 @@ class GramCache:
             ptr, ldx, seg_rows, seg_stride = keep.data_ptr(), d, 0, 0
         g = self.buffers.get(name)
         if g is None:
-            g = self.buffers[name] = torch.zeros(d, d, dtype=torch.float32, device=self.device)
+            g = self.buffers[name] = torch.zeros(d, d, dtype=self.dtype, device=self.device)
         elif g.shape[0] != d:
             raise RuntimeError(f"{name}: activation width changed from {g.shape[0]} to {d}")
         self.calls[name] += 1
@@ -179,6 +185,10 @@ class GramCache:
         self._finalized = False
         code = _DTYPES[keep.dtype]
         nbytes = rows * ldx * elem
+        if self.precision == "fp64":
+            _lib.check(self._lib.vlm_syrk_accum_f64(ptr, code, rows, d, ldx, seg_rows, seg_stride,
+                                                    g.data_ptr(), g.stride(0), self._launch_stream(keep)))
+            return
         if 0 < nbytes <= self.defer_bytes and not simt:
             self._pending.append((code, keep, g, ptr, rows, d, ldx, seg_rows, seg_stride))
             self._pending_bytes += nbytes
@@ -282,7 +292,7 @@ class GramCache:
         if not named_dims:
             return
         total = sum(d * d for _, d in named_dims)
-        arena = torch.zeros(total, dtype=torch.float32, device=self.device)
+        arena = torch.zeros(total, dtype=self.dtype, device=self.device)
         off = 0
         for name, d in named_dims:
             self.buffers[name] = arena[off: off + d * d].view(d, d)
@@ -314,7 +324,10 @@ class GramCache:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         for name in self.live_names():
             g = self.buffers[name]
-            _lib.check(self._lib.vlm_sym_finalize(g.data_ptr(), g.shape[0], g.stride(0), None, 0, stream))
+            if self.dtype == torch.float64:
+                _lib.check(self._lib.vlm_sym_finalize_f64(g.data_ptr(), g.shape[0], g.stride(0), stream))
+            else:
+                _lib.check(self._lib.vlm_sym_finalize(g.data_ptr(), g.shape[0], g.stride(0), None, 0, stream))
         self._finalized = True
 
     def gram(self, name):
@@ -331,7 +344,9 @@ class GramCache:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         for name in self.live_names():
             g = self.buffers[name]
-            if dtype == torch.float64:
+            if self.dtype == torch.float64:
+                out[name] = g.to(device=device, dtype=dtype, copy=True)
+            elif dtype == torch.float64:
                 wide = torch.empty(g.shape, dtype=torch.float64, device=self.device)
                 _lib.check(self._lib.vlm_sym_finalize(g.data_ptr(), g.shape[0], g.stride(0), wide.data_ptr(),
                                                       wide.stride(0), stream))
@@ -348,6 +363,8 @@ class GramCache:
         """The packed fp32 upper-triangle container (gramfile.py): a quarter of the reference file's bytes;
         regmean reads either format.  Returns the number of bytes written."""
         from . import gramfile
+        if self.dtype == torch.float64:
+            raise RuntimeError("the packed container holds fp32 values: write fp64 Grams with save() (the reference's format)")
         return gramfile.save_packed(self, path)
 
     def reset(self):
