@@ -95,9 +95,51 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm)}
 
 
+def ncu_dram_traffic(name):
+    """dram read + write bytes of one launch from a committed `ncu --set full` summary under profiles/ (or None)."""
+    prof = os.path.join(ROOT, "profiles", name)
+    if not os.path.exists(prof):
+        return None
+    vals = {}
+    for line in open(prof):
+        parts = line.strip().split(",")
+        if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            vals[parts[0]] = float(parts[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(parts[1], 1.0)
+    return int(sum(vals.values())) if len(vals) == 2 else None
+
+
 # ---------------------------------------------------------------------------------------------------
 def syrk_flops(rows, d):
     return rows * d * (d + 1)  # symmetric count, SURVEY.md §8(d)
+
+
+def make_timed_cache(vlm):
+    class TimedCache(vlm.GramCache):
+        """GramCache that brackets every vlm_syrk_accum launch with CUDA events on the launching stream."""
+        events, timing = [], False
+
+        def accumulate(self, name, x):
+            rows = x.numel() // x.shape[-1]
+            if not self.timing or 0 < x.numel() * x.element_size() <= self.defer_bytes:
+                return super().accumulate(name, x)   # deferred activations are timed in flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            super().accumulate(name, x)
+            b.record()
+            self.events.append((a, b, syrk_flops(rows, x.shape[-1]), f"{rows}x{x.shape[-1]}:{str(x.dtype).replace('torch.', '')}", 1))
+
+        def flush(self):
+            if not self.timing or not self._pending:
+                return super().flush()
+            flops = sum(syrk_flops(p[4], p[5]) for p in self._pending)   # (rows, d) of each pending problem
+            n = len(self._pending)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            super().flush()
+            b.record()
+            self.events.append((a, b, flops, "grouped launches (text Grams + 768-wide image Grams)", n))
+
+    return TimedCache
 
 
 def run_ours(args):
@@ -126,31 +168,7 @@ def run_ours(args):
     vlm.init_synthetic_(model.eval(), seed=1)
     amp = {"fp32": None, "bf16": torch.bfloat16, "fp16": torch.float16}[args.autocast]
 
-    class TimedCache(vlm.GramCache):
-        """GramCache that brackets every vlm_syrk_accum launch with CUDA events on the launching stream."""
-        events, timing = [], False
-
-        def accumulate(self, name, x):
-            rows = x.numel() // x.shape[-1]
-            if not self.timing or 0 < x.numel() * x.element_size() <= self.defer_bytes:
-                return super().accumulate(name, x)   # deferred activations are timed in flush()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            super().accumulate(name, x)
-            b.record()
-            self.events.append((a, b, syrk_flops(rows, x.shape[-1]), f"{rows}x{x.shape[-1]}:{str(x.dtype).replace('torch.', '')}", 1))
-
-        def flush(self):
-            if not self.timing or not self._pending:
-                return super().flush()
-            flops = sum(syrk_flops(p[4], p[5]) for p in self._pending)   # (rows, d) of each pending problem
-            n = len(self._pending)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            super().flush()
-            b.record()
-            self.events.append((a, b, flops, "grouped launches (text Grams + 768-wide image Grams)", n))
-
+    TimedCache = make_timed_cache(vlm)
     cache = TimedCache(dev, defer_bytes=args.defer_mb << 20, max_pending_bytes=args.defer_cap_mb << 20)
     cache.register(model, use_moe=True)
     B = args.batch
@@ -249,6 +267,7 @@ def run_ours(args):
     ms, t0, t1, ar_ms = timed(lambda i: step(dev_batches[i % 2]), args.steps, with_allreduce=True)
     cache.timing = False
     launches = vlm._lib.launch_count() - launches0
+    n_live, reduce_bytes = len(cache.live_names()), getattr(cache, "last_reduce_bytes", 0)
     clocks = sampler.stop(t0, t1) if sampler else None
     value = world * B * args.steps / (ms * 1e-3)
 
@@ -268,22 +287,14 @@ def run_ours(args):
     n_ev = max(len(cache.events), 1)
     # DRAM traffic per launch of the dominant shape (36928 x 3072 fp32) from the committed ncu --set full capture
     traffic = None
-    prof = os.path.join(ROOT, "profiles", "r01_syrk_tc2_f32_36928x3072.summary.csv")
-    if os.path.exists(prof):
-        vals = {}
-        for line in open(prof):
-            parts = line.strip().split(",")
-            if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                vals[parts[0]] = float(parts[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(parts[1], 1.0)
-        if len(vals) == 2:
-            traffic = int(sum(vals.values()))
+    traffic = ncu_dram_traffic("r02_syrk_2sm_f32_36928x3072.summary.csv") or ncu_dram_traffic("r01_syrk_tc2_f32_36928x3072.summary.csv")
     sixteen = amp is not None
     # TF32 runs at half the bf16 tensor rate; the MEASURED bf16 figure (sustained: kernel timed inside a long step)
     peak_tf = peaks["bf16_tflops_sustained"] * (1.0 if sixteen else 0.5)
     achieved_tf = tot_flops / (tot_ms * 1e-3) * 1e-12 if tot_ms > 0 else 0.0
     roofline = {
-        "kernel": "syrk_tc2_kernel (CTA pairs, TMA multicast, tcgen05 kind::tf32, TMEM accumulators, TMA reduce-add)" if not sixteen
-        else "syrk_tc2_kernel (mixed kind::tf32 / kind::f16 launches under autocast)",
+        "kernel": "syrk_2sm_kernel (CTA pairs, one tcgen05.mma.cta_group::2 kind::tf32 stream per pair, TMA loads, TMEM accumulators, TMA reduce-add)" if not sixteen
+        else "syrk_2sm_kernel (mixed kind::tf32 / kind::f16 launches under autocast)",
         "bound": "tensor", "achieved": round(achieved_tf, 2), "peak": round(peak_tf, 1), "unit": "TFLOP/s",
         "frac": round(achieved_tf / peak_tf, 4), "traffic": traffic,
         "traffic_note": "dram read+write bytes of ONE 36928x3072 fp32 launch (ncu --set full, profiles/); its algorithmic minimum is one read of X = 453.8 MB",
@@ -306,19 +317,50 @@ def run_ours(args):
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * B * 4}
 
     # ---- Gram parity spot check on the bench's own activations (cheap; not timed) ------------------
-    parity = None
-    if rank == 0:
+    L = cfg["num_layers"]
+    parity_names = ["transformer.blocks.0.attn.v", f"transformer.blocks.{L - 1}.mlp.v.fc2", f"transformer.blocks.{L // 2 - 1}.mlp.l.fc1"]
+
+    def fp64_probes(names, store):
+        """The reference hook's arithmetic (cache_gram_matrices.py:250-253) on the device, for a few modules."""
+        mods = dict(model.named_modules())
+
+        def probe(m, i, o):
+            x = (i[0] if isinstance(i, tuple) else i).double()
+            x = x.reshape(-1, x.shape[-1])
+            store[m.module_name] = store.get(m.module_name, 0) + x.T @ x
+        return [mods[n].register_forward_hook(probe) for n in names]
+
+    def gram_parity(vamp=amp):
         cache.reset()
         probe = {}
-        mods = dict(model.named_modules())
-        names = ["transformer.blocks.0.attn.v", "transformer.blocks.11.mlp.v.fc2", "transformer.blocks.5.mlp.l.fc1"]
-        hs = [mods[n].register_forward_hook(lambda m, i, o, n=n: probe.__setitem__(
-            n, (lambda x: x.double().reshape(-1, x.shape[-1]).T @ x.double().reshape(-1, x.shape[-1]))(i[0] if isinstance(i, tuple) else i)))
-            for n in names]
-        step(dev_batches[0])
+        hs = fp64_probes(parity_names, probe)
+        step(dev_batches[0], vamp)
         for h in hs:
             h.remove()
-        parity = {n: float(((cache.gram(n).double() - probe[n]).norm() / probe[n].norm()).item()) for n in names}
+        out = {n: float(((cache.gram(n).double() - probe[n]).norm() / probe[n].norm()).item()) for n in parity_names}
+        cache.reset()
+        return out
+
+    parity = gram_parity() if rank == 0 else None
+
+    # ---- N > 1: the REDUCED Grams against the sum of per-rank fp64 reference-hook Grams (every rank checks) ----
+    reduced_parity = None
+    if world > 1:
+        cache.reset()
+        probe = {}
+        hs = fp64_probes(parity_names, probe)
+        step(dev_batches[0])                     # every rank its own shard of the calibration set
+        for h in hs:
+            h.remove()
+        cache.all_reduce(group)
+        errs = []
+        for n in parity_names:
+            ref = probe[n].clone()
+            dist.all_reduce(ref)                 # fp64 sum over the ranks = the single-process reference Gram
+            errs.append((cache.gram(n).double() - ref).norm() / ref.norm())
+        worst = torch.stack(errs).max()
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        reduced_parity = float(worst.item())
         cache.reset()
 
     # ---- informational: the same calibration with faster stock-torch forwards ----------------------
@@ -349,6 +391,37 @@ def run_ours(args):
             "value": round(world * B * args.steps / (vms * 1e-3), 2), "unit": "samples/s", "ms_per_step": round(vms / args.steps, 3)}
         cache.set_side_stream(False)
         cache.reset()
+        # the public default, GramCache(): every Gram launched from its hook (defer_bytes = 0)
+        saved_defer, cache.defer_bytes = cache.defer_bytes, 0
+        for i in range(3):
+            step(dev_batches[i % 2])
+        cache.reset()
+        cache.timing, cache.events = True, []
+        vms, _, _, _ = timed(lambda i: step(dev_batches[i % 2]), args.steps, with_allreduce=True)
+        cache.timing = False
+        sy_ms = sum(a.elapsed_time(b) for a, b, *_ in cache.events)
+        sy_fl = sum(e[2] for e in cache.events)
+        variants["default_api_one_launch_per_hook"] = {
+            "value": round(world * B * args.steps / (vms * 1e-3), 2), "unit": "samples/s", "ms_per_step": round(vms / args.steps, 3),
+            "syrk_tflops": round(sy_fl / (sy_ms * 1e-3) * 1e-12, 1) if sy_ms > 0 else None, "syrk_launches_timed": len(cache.events)}
+        cache.defer_bytes = saved_defer
+        cache.reset()
+        # the reference's own calibration precision: PL precision=16 autocast (src/vilt/config.py:116) with the
+        # reference's explicit attention — hook inputs are a mix of fp32 (LayerNorm outputs) and fp16 (attention /
+        # GELU outputs), the latter on the kind::f16 tensor path
+        for m in attn_mods:
+            m.attn_impl = "reference"
+        for i in range(3):
+            step(dev_batches[i % 2], torch.float16)
+        cache.reset()
+        vms, _, _, _ = timed(lambda i: step(dev_batches[i % 2], torch.float16), args.steps, with_allreduce=True)
+        variants["autocast_fp16_reference_attention"] = {
+            "value": round(world * B * args.steps / (vms * 1e-3), 2), "unit": "samples/s", "ms_per_step": round(vms / args.steps, 3),
+            "gram_parity_rel_fro": gram_parity(torch.float16) if rank == 0 else None,
+            "note": "the reference's own precision (fp16 autocast, mixed fp32 / fp16 hook inputs); parity vs the fp64 hook on the same activations"}
+        for m in attn_mods:
+            m.attn_impl = args.attn
+        cache.reset()
 
     # ---- kernel (b): interpolation merge of this checkpoint ---------------------------------------
     merge = bench_merge(vlm, model, cfg, dev, group, world, rank, peaks, args)
@@ -362,6 +435,8 @@ def run_ours(args):
         if world > 1:
             cache.all_reduce(group)
         regmean = bench_regmean(vlm, model, cfg, cache, dev, group, world, args)
+        if world == 1 and args.model == "base":
+            regmean.update(bench_regmean_chain(vlm, model, cfg, cache, dev, step, dev_batches, B))
         if world == 1 and not args.no_gramfile:
             gram_file = bench_gramfile(vlm, cache, dev)
         cache.reset()
@@ -402,7 +477,8 @@ def run_ours(args):
                          "the l / v experts (read in place, 4-D TMA), layers >= vlffn_start run the vl experts"}
         cache.reset()
 
-    irtr = bench_irtr(vlm, model, cfg, dev, group, world, args) if args.irtr else None
+    irtr = bench_irtr(vlm, model, cfg, dev, group, world, args) if (args.irtr or (args.model == "base" and not args.no_irtr)) else None
+    vitl = bench_vitl(vlm, dev, group, world, args) if (args.model == "base" and not args.no_vitl) else None
 
     # ---- the reference's own hook, unchanged, with the model on the B200 (the GPU-vs-GPU "before") ----
     ref_gpu = None
@@ -423,9 +499,12 @@ def run_ours(args):
                        "gram_hooks": (f"activations <= {args.defer_mb} MB are held by reference and issued as grouped launches "
                                       f"(flush at {args.defer_cap_mb} MB pending and after every forward); larger ones launch "
                                       "from the hook") if args.defer_mb > 0 else "one SYRK launch per hook call",
-                       "allreduce_ms_in_timed_region": round(ar_ms, 3)},
+                       "allreduce_ms_in_timed_region": round(ar_ms, 3),
+                       "allreduce": (f"packed upper triangles of the {n_live} live Grams in one NCCL all-reduce "
+                                     f"({reduce_bytes / 1e6:.0f} MB)") if world > 1 else None},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "merge": merge, "reference_hook_on_gpu": ref_gpu, "regmean": regmean, "gram_file": gram_file, "fused_route": fused, "irtr": irtr, "gram_parity_rel_fro": parity,
+            "roofline": roofline, "merge": merge, "reference_hook_on_gpu": ref_gpu, "regmean": regmean, "gram_file": gram_file, "fused_route": fused, "irtr": irtr, "vitl": vitl, "gram_parity_rel_fro": parity,
+            "gram_parity_rel_fro_reduced": reduced_parity,
             "forward_variants": variants,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -485,32 +564,49 @@ def bench_merge(vlm, model, cfg, dev, group, world, rank, peaks, args):
     lib.vlm_merge_plan_destroy(plan)
     gbs = nbytes / (ms * 1e-3) * 1e-9
 
-    # end to end through the public API: pinned host state_dict in, merged host tensors out
+    # end to end through the public API: pinned host state_dict in, merged host tensors out.  N > 1: every rank stages
+    # and merges its shard, one all-gather leaves the result on every GPU, and the HOST copy is made once (rank 0) —
+    # N simultaneous device->host copies of the same 340 MB into one host's memory were slower than one GPU
+    # (profiles/r01_bench_n8.json: 28.9 vs 53.0 GB/s)
     host_sd = {k: (v.cpu().pin_memory() if "transformer.blocks" in k else v.cpu()) for k, v in sd.items()}
-    vlm.merge_weights(host_sd, mcfg, device=dev, num_layers=L, group=group)
+    out_dev = "cpu" if rank == 0 else "cuda"
+    vlm.merge_weights(host_sd, mcfg, device=dev, num_layers=L, group=group, out_device=out_dev)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     stats = {}
-    merged = vlm.merge_weights(host_sd, mcfg, device=dev, num_layers=L, group=group, stats=stats)
+    merged = vlm.merge_weights(host_sd, mcfg, device=dev, num_layers=L, group=group, stats=stats, out_device=out_dev)
     torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([dt], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = t.item()
+    # N > 1: the tensor-sharded merge + all-gather against the same merge done locally on this rank, every tensor
+    sharded_equal = None
+    if world > 1:
+        local = vlm.merge_weights(sd, mcfg, device=dev, num_layers=L)
+        shard = vlm.merge_weights(sd, mcfg, device=dev, num_layers=L, group=group)
+        eq = torch.tensor([int(all(torch.equal(local[op.dst], shard[op.dst]) for op in ops))], device=dev)
+        dist.all_reduce(eq, op=dist.ReduceOp.MIN)
+        sharded_equal = bool(eq.item())
+        del local, shard
     k0 = "transformer.blocks.0.mlp.fc1.weight"
-    ok = torch.equal(merged[k0], 0.5 * host_sd["transformer.blocks.0.mlp.v.fc1.weight"] + 0.5 * host_sd["transformer.blocks.0.mlp.l.fc1.weight"])
+    ok = torch.equal(merged[k0].cpu(), 0.5 * host_sd["transformer.blocks.0.mlp.v.fc1.weight"] + 0.5 * host_sd["transformer.blocks.0.mlp.l.fc1.weight"])
     return {
         "metric": "merge_GBps", "workload": f"linear interpolation alpha=0.5, VLMo-{args.model} all_moe -> ufo, IRTR-used experts "
                                             f"({len(ops)} tensors, {nbytes / 1e6:.1f} MB algorithmic: read 2 experts + write 1 per layer)",
         "value": round(gbs, 1), "unit": "GB/s", "ms_per_launch": round(ms, 4), "launches_per_merge": 1,
         "roofline": {"kernel": "merge_segments_kernel", "bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"],
-                     "unit": "GB/s", "frac": round(gbs / peaks["hbm_gbs"], 4), "traffic": None,
+                     "unit": "GB/s", "frac": round(gbs / peaks["hbm_gbs"], 4),
+                     "traffic": ncu_dram_traffic("r01_merge_wsum2_85M.summary.csv") if args.model == "base" else None,
+                     "traffic_note": "dram read+write bytes of one launch of this workload (ncu --set full, profiles/r01_merge_wsum2_85M.summary.csv); algorithmic bytes = " + str(nbytes),
                      "peak_source": f"{peaks['source']}: hbm_gbs (burst copy)", "frac_of_nominal_8TBps": round(gbs / 8000.0, 4)},
         "e2e": {"value": round(nbytes / dt * 1e-9, 2), "unit": "GB/s", "seconds": round(dt, 4),
-                "h2d_bytes": stats.get("h2d_bytes"), "d2h_bytes": stats.get("d2h_bytes"), "bit_exact_vs_torch": bool(ok)},
+                "h2d_bytes": stats.get("h2d_bytes"), "d2h_bytes": stats.get("d2h_bytes"), "bit_exact_vs_torch": bool(ok),
+                "host_copy": "rank 0 only; the other ranks keep the gathered result on their GPU" if world > 1 else "this rank"},
+        "sharded_bit_equal_to_local": sharded_equal,
     }
 
 
@@ -553,18 +649,16 @@ def bench_irtr(vlm, model, cfg, dev, group, world, args, n_img=5000, per_img=5, 
 
 def bench_regmean(vlm, model, cfg, cache, dev, group, world, args):
     """RegMean of the bench checkpoint with the Grams just cached on the device (scaling_for_non_diag = 0.9):
-    wall time of the whole merge, split into the W*Ghat GEMMs (kernel (c), fp64 DMMA) and the SPD solves
-    (cuSOLVER), plus one linear checked against torch fp64 on the same Grams."""
+    wall time of the whole merge with the linear problems spread over 8 streams (three repeats), and the W*Ghat
+    GEMMs (kernel (c), fp64 DMMA) / SPD solves (cuSOLVER) split from a one-stream run, timed with CUDA events on
+    that stream; one linear checked against torch fp64 on the same Grams."""
     import torch.distributed as dist
 
     mcfg = dict(vlffn_start_layer_index=cfg["vlffn_start_layer_index"], scaling_for_non_diag=0.9,
                 loss_names={"irtr": 1, "vqa": 0, "nlvr2": 0})
     sd = {k: v.detach() for k, v in model.state_dict().items()}
     L = cfg["num_layers"]
-    vlm.regmean(sd, mcfg, device=dev, num_layers=L, group=group, gram_matrices=cache)  # warm-up (cuSOLVER handle, plans)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
+
     def run(streams):
         stats = {}
         if world > 1:
@@ -577,10 +671,10 @@ def bench_regmean(vlm, model, cfg, cache, dev, group, world, args):
         return time.perf_counter() - t0, stats, out
 
     NS = 8
-    run(1)                      # warm-up of the sequential path too
-    runs = [run(NS) for _ in range(2)]  # best of two: cuSOLVER / lazy module loading can leave stragglers after the warm-up
+    run(NS)                     # warm-up: cuSOLVER handles + workspaces per stream, lazy module loading
+    run(1)
+    runs = [run(NS) for _ in range(3)]
     dt, _, merged = min(runs, key=lambda r: r[0])
-    # sequential: the only mode with a meaningful rhs / solve split (best of two as well)
     dt_seq, stats, merged_seq = min((run(1) for _ in range(2)), key=lambda r: r[0])
     same = all(torch.equal(merged[k], merged_seq[k]) for k in merged)
     # check: layer 0 attention projection, torch fp64 on the same device Grams
@@ -596,59 +690,255 @@ def bench_regmean(vlm, model, cfg, cache, dev, group, world, args):
     err = ((got - want).norm() / want.norm()).item()
     d, h = cfg["hidden_size"], cfg["hidden_size"] * cfg["mlp_ratio"]
     rhs_flops = L * 2 * 2 * (3 * d * d * d + d * d * d + h * d * d + d * h * h)
-    return {"seconds": round(dt, 4), "seconds_both_runs": [round(r[0], 4) for r in runs], "solve_streams": NS,
+    secs = sorted(r[0] for r in runs)
+    return {"seconds": round(dt, 4), "seconds_all_runs": [round(r[0], 4) for r in runs],
+            "spread": round(secs[-1] / secs[0] - 1.0, 3), "solve_streams": NS,
             "seconds_sequential": round(dt_seq, 4), "concurrent_equals_sequential": bool(same),
             "rhs_seconds": round(stats.get("rhs_seconds", 0.0), 4),
             "solve_seconds": round(stats.get("solve_seconds", 0.0), 4),
             "rhs_fp64_tflops": round(rhs_flops / max(stats.get("rhs_seconds", 1e-9), 1e-9) * 1e-12 / world, 2),
             "linear_problems": 4 * L, "dtype": "f64", "check_rel_err_vs_torch_fp64": err,
-            "note": "RHS = fp64 DMMA kernel incl. scale_G and sum of Grams; solve = cuSOLVER potrf/potrs (off the hot path); "
-                    "seconds = the linear problems spread over 8 streams, rhs/solve split from the sequential run"}
+            "note": "RHS = fp64 DMMA kernel incl. scale_G and the sum of Grams; solve = cuSOLVER potrf/potrs (off the hot path); "
+                    "seconds = host wall clock of the whole merge, linear problems spread over 8 streams; rhs / solve seconds = "
+                    "CUDA-event time of those launches in the one-stream run"}
+
+
+def bench_regmean_chain(vlm, model, cfg, cache, dev, step, dev_batches, B):
+    """Config 3 END TO END on identical activations: forward hooks -> device Grams -> regmean, against the reference
+    formula (scale_G, sum, explicit inverse in fp64: vilt_module.py:388-392, :423-434) fed with the fp64 Grams of
+    the reference hook (cache_gram_matrices.py:250-253) taken on the same activations.  Two calibration steps of
+    64 samples: 5,120 text rows >= 3,072, every summed Gram is full rank.  Checked linears: all four of the first and
+    the last layer (768- and 3072-wide).  Also the calibration throughput of the Gram precision modes."""
+    L = cfg["num_layers"]
+    layers = sorted({0, L - 1})
+    c64 = vlm.GramCache(dev, precision="fp64")
+    c64.register(model, use_moe=True)
+    ref, mods = {}, dict(model.named_modules())
+    names = [f"transformer.blocks.{i}.{t}" for i in layers for m in ("v", "l")
+             for t in (f"attn.{m}", f"attn.{m}.proj", f"mlp.{m}.fc1", f"mlp.{m}.fc2")]
+
+    def probe(m, i, o):
+        x = (i[0] if isinstance(i, tuple) else i).double()
+        x = x.reshape(-1, x.shape[-1])
+        ref[m.module_name] = ref.get(m.module_name, 0) + x.T @ x
+
+    cache.reset()
+    hs = [mods[n].register_forward_hook(probe) for n in names]
+    for i in range(2):
+        step(dev_batches[i % 2])
+    for h in hs:
+        h.remove()
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    out = {}
+    worst = {"fp64": 0.0, "tf32": 0.0}
+    detail = {}
+    for alpha in (1.0, 0.9):
+        mcfg = dict(vlffn_start_layer_index=cfg["vlffn_start_layer_index"], scaling_for_non_diag=alpha,
+                    loss_names={"irtr": 1, "vqa": 0, "nlvr2": 0})
+        merged = {"fp64": vlm.regmean(sd, mcfg, device=dev, num_layers=L, gram_matrices=c64),
+                  "tf32": vlm.regmean(sd, mcfg, device=dev, num_layers=L, gram_matrices=cache)}
+        for i in layers:
+            for tgt, wk, gk in ((f"transformer.blocks.{i}.attn.qkv.weight", "transformer.blocks.{i}.attn.{m}.qkv.weight", "transformer.blocks.{i}.attn.{m}"),
+                                (f"transformer.blocks.{i}.attn.proj.weight", "transformer.blocks.{i}.attn.{m}.proj.weight", "transformer.blocks.{i}.attn.{m}.proj"),
+                                (f"transformer.blocks.{i}.mlp.fc1.weight", "transformer.blocks.{i}.mlp.{m}.fc1.weight", "transformer.blocks.{i}.mlp.{m}.fc1"),
+                                (f"transformer.blocks.{i}.mlp.fc2.weight", "transformer.blocks.{i}.mlp.{m}.fc2.weight", "transformer.blocks.{i}.mlp.{m}.fc2")):
+                num = den = 0
+                for m in ("v", "l"):
+                    g = ref[gk.format(i=i, m=m)]
+                    gh = alpha * g + (1 - alpha) * torch.diag_embed(torch.diagonal(g))      # scale_G
+                    num = num + sd[wk.format(i=i, m=m)].double() @ gh
+                    den = den + gh
+                want = num @ torch.inverse(den)                                              # :432-434
+                for mode in merged:
+                    e = float(((merged[mode][tgt] - want).norm() / want.norm()).item())
+                    worst[mode] = max(worst[mode], e)
+                    detail[f"{mode} a={alpha} {tgt.split('blocks.')[1]}"] = float(f"{e:.3e}")
+    out["e2e_rel_err_vs_fp64_grams"] = worst["fp64"]
+    out["e2e_rel_err_vs_fp64_grams_single_pass_tf32"] = worst["tf32"]
+    out["e2e_detail"] = detail
+    out["e2e_note"] = ("whole chain on identical activations: hooks -> device Grams -> regmean vs the reference formula on the "
+                       "reference hook's fp64 Grams; worst of 8 linears (layers 0 and L-1) x scaling_for_non_diag in {1.0, 0.9}. "
+                       "e2e_rel_err_vs_fp64_grams = GramCache(precision='fp64') (the RegMean-grade mode, BASELINE 1e-4); "
+                       "single_pass_tf32 = the default fast mode (Gram tolerance 1e-3)")
+    gram_err = max(float(((c64.gram(n) - g).norm() / g.norm()).item()) for n, g in ref.items())
+    out["fp64_mode_gram_rel_fro"] = gram_err
+
+    # calibration throughput of the precision modes (same forward, same batches; CUDA events, 3 steps each)
+    cache.enabled = False
+    modes = {}
+    c3 = vlm.GramCache(dev, precision="tf32x3", defer_bytes=cache.defer_bytes, max_pending_bytes=cache.max_pending_bytes)
+    c3.register(model, use_moe=True)
+    for mode, c, other in (("fp64", c64, c3), ("tf32x3", c3, c64)):
+        other.enabled, c.enabled = False, True
+        c.reset()
+        step(dev_batches[0])
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(3):
+            step(dev_batches[(i + 1) % 2])
+        b.record()
+        torch.cuda.synchronize(dev)
+        modes[mode] = {"value": round(3 * B / (a.elapsed_time(b) * 1e-3), 2), "unit": "samples/s",
+                       "ms_per_step": round(a.elapsed_time(b) / 3, 2)}
+    c64.remove_hooks()
+    c3.remove_hooks()
+    del c64, c3
+    cache.enabled = True
+    cache.reset()
+    out["gram_precision_modes"] = modes
+    return out
+
+
+def bench_vitl(vlm, dev, group, world, args, B=32, steps=4):
+    """Config 5: ViT-L/16 multiway (24 layers, 1024 / 4096 wide, vl experts from layer 21): Gram caching at B = 32 per
+    GPU (+ the one all-reduce at N > 1), one 4096-wide Gram checked against the fp64 hook, then the RegMean merge
+    of the 96 linear problems (sharded over the ranks) from those Grams."""
+    import torch.distributed as dist
+
+    cfg = vlm.vlmo_config("large", attn_impl=args.attn)
+    with torch.device(dev):
+        model = vlm.VLMo(cfg)
+    vlm.init_synthetic_(model.eval(), seed=1)
+    rank = dist.get_rank(group) if group is not None else 0
+    cache = make_timed_cache(vlm)(dev, defer_bytes=args.defer_mb << 20, max_pending_bytes=args.defer_cap_mb << 20)
+    cache.register(model, use_moe=True)
+    batches = [vlm.synthetic_batch(B, cfg, seed=4321 + rank * 16 + i, device=dev) for i in range(2)]
+
+    def step(i):
+        with torch.no_grad():
+            model(batches[i % 2])
+
+    for i in range(2):
+        step(i)
+    if world > 1:
+        cache.all_reduce(group)
+    cache.reset()
+    # parity of one 4096-wide Gram on identical activations
+    name = "transformer.blocks.23.mlp.v.fc2"
+    probe = {}
+    h = dict(model.named_modules())[name].register_forward_hook(
+        lambda m, i, o: probe.__setitem__("g", (lambda x: x.T @ x)(i[0].double().reshape(-1, i[0].shape[-1]))))
+    step(0)
+    h.remove()
+    err = float(((cache.gram(name).double() - probe["g"]).norm() / probe["g"].norm()).item())
+    del probe
+    cache.reset()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    cache.timing, cache.events = True, []
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        step(i)
+    if world > 1:
+        cache.all_reduce(group)
+    b.record()
+    torch.cuda.synchronize(dev)
+    cache.timing = False
+    ms = a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    sy_ms = sum(x.elapsed_time(y) for x, y, *_ in cache.events)
+    sy_fl = sum(e[2] for e in cache.events)
+    # RegMean from these Grams: text rows = steps x 32 x 40 x world >= 4096 -> every summed Gram is full rank
+    mcfg = dict(vlffn_start_layer_index=cfg["vlffn_start_layer_index"], scaling_for_non_diag=0.9,
+                loss_names={"irtr": 1, "vqa": 0, "nlvr2": 0})
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    rm = []
+    for _ in range(2):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        merged = vlm.regmean(sd, mcfg, device=dev, num_layers=24, group=group, gram_matrices=cache)
+        torch.cuda.synchronize(dev)
+        rm.append(time.perf_counter() - t0)
+    finite = bool(torch.isfinite(merged["transformer.blocks.23.mlp.fc2.weight"]).all().item())
+    out = {"value": round(world * B * steps / (ms * 1e-3), 2), "unit": "samples/s", "ms_per_step": round(ms / steps, 2),
+           "batch_per_gpu": B, "steps": steps, "grams": len(cache.live_names()),
+           "syrk_tflops": round(sy_fl / (sy_ms * 1e-3) * 1e-12, 1) if sy_ms > 0 else None,
+           "syrk_share_of_step": round(sy_ms / ms, 4), "gram_parity_rel_fro_4096": err,
+           "regmean_seconds": round(min(rm), 4), "regmean_linear_problems": 96, "regmean_finite": finite,
+           "workload": "VLMo-large all_moe (ViT-L/16 multiway, 24 layers, 51 experts), 192 Grams (144 x 1024^2 + 48 x 4096^2)"}
+    cache.remove_hooks()
+    del model, cache, sd, merged
+    torch.cuda.empty_cache()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
-def cpu_reference_step(model, cfg, batch_size, seed, store):
-    """The reference's CPU implementation of one calibration step: stock forward on the host + the reference
-    hook (fp64 cast, fp64 matmul, host accumulate) restated in oracle.reference_hook_torch."""
-    import vl_merging_b200 as vlm
-
-    batch = vlm.synthetic_batch(batch_size, cfg, seed=seed)
-    with torch.no_grad():
-        model(batch)
-    return batch_size
+REF_BATCH = 4   # samples per reference-arm step (BASELINE.md §3), bounded so that --steps K --warmup W ends within minutes
 
 
 def build_cpu_reference(model_name):
+    """The reference's CPU implementation of the path.  Where the reference sources are present (the build
+    container: /root/reference/src, or $VLM_REFERENCE_SRC) this is the UNMODIFIED reference — ViLTransformerSS
+    built like src/run.py:165-185, its own hook registered by the loop of src/cache_gram_matrices.py:264-281 —
+    imported through the stand-ins of oracle/ref_shims (kind "reference").  On the GPU box the sources are absent
+    and the arm falls back to the port: the stock-torch mirror of the forward + the hook restated in oracle/
+    (kind "port").  Returns (kind, cfg, step(batch_size, seed) -> samples, store)."""
     import oracle
     import vl_merging_b200 as vlm
     from vl_merging_b200.gram import select_hooked_modules
 
     torch.set_num_threads(os.cpu_count() or 1)
     cfg = vlm.vlmo_config(model_name)
-    model = vlm.init_synthetic_(vlm.VLMo(cfg).eval(), seed=1)
     store = oracle.new_gram_store()
-    hook = oracle.reference_hook_torch(store)
-    for name, module in select_hooked_modules(model, use_moe=True):
-        module.module_name = name
-        module.register_forward_hook(hook)
-    return cfg, model, store
+    kind = "port"
+    model = None
+    try:
+        import ref_harness as rh
+        if rh.reference_available() and model_name in ("base", "large") and not os.environ.get("VLM_BENCH_FORCE_PORT"):
+            named = {"base": "task_finetune_irtr_coco_square_randaug_base_image384",
+                     "large": "task_finetune_irtr_f30k_square_randaug_large_image384"}[model_name]
+            ref_cfg = rh.make_config([named, "all_moe"], load_path="", random_initialization=True, per_gpu_batchsize=REF_BATCH)
+            model = rh.build_model(ref_cfg)
+            rh.ref_register_gram_hooks(model, store, use_moe=True)
+            kind = "reference"
+    except Exception as e:   # the stand-ins do not cover this environment: say so and time the port
+        print(f"# reference import failed ({type(e).__name__}: {e}); timing the port", file=sys.stderr)
+        model = None
+        store = oracle.new_gram_store()
+    if model is None:
+        model = vlm.init_synthetic_(vlm.VLMo(cfg).eval(), seed=1)
+        hook = oracle.reference_hook_torch(store)
+        for name, module in select_hooked_modules(model, use_moe=True):
+            module.module_name = name
+            module.register_forward_hook(hook)
+
+    def step(batch_size, seed):
+        batch = vlm.synthetic_batch(batch_size, cfg, seed=seed)
+        with torch.no_grad():
+            if kind == "reference":   # the two towers compute_irtr runs per validation batch (objectives.py:372-470)
+                model.infer_text_ft(batch)
+                model.infer_image_ft(batch)
+            else:
+                model(batch)
+        return batch_size
+
+    return kind, cfg, step, store
 
 
 def cpu_baseline_sample(model_name, budget_s=25.0):
-    cfg, model, store = build_cpu_reference(model_name)
+    kind, cfg, step, store = build_cpu_reference(model_name)
     t0 = time.perf_counter()
-    cpu_reference_step(model, cfg, 1, 0, store)  # warm-up (also sizes the sample)
+    step(1, 0)  # warm-up (also sizes the sample)
     warm = time.perf_counter() - t0
-    n = max(1, min(8, int(budget_s / max(warm, 1e-3)) - 1))
+    per = REF_BATCH if warm * REF_BATCH * 2 < budget_s else 1
+    n = max(1, min(8, int(budget_s / max(warm * per, 1e-3)) - 1))
     t0 = time.perf_counter()
     done = 0
     for i in range(n):
-        done += cpu_reference_step(model, cfg, 1, 100 + i, store)
+        done += step(per, 100 + i)
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return {"value": round(done / dt, 4), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{done} calibration step(s) of 1 sample (577+40 tokens, {len(store)} fp64 Grams) of the same VLMo-{model_name} workload, "
+    return {"value": round(done / dt, 4), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{done // per} calibration step(s) of {per} sample(s) (577+40 tokens each, {len(store)} fp64 Grams) of the same VLMo-{model_name} workload, "
                       f"stock forward + reference hook on the host, after 1 warm-up step",
             "cpu_model": cpu_model_name()}
 
@@ -668,24 +958,25 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
-    cfg, model, store = build_cpu_reference(args.model)
-    per_step = 1  # bounded sample: one sample per step keeps --steps K --warmup W within minutes on the host
+    kind, cfg, step, store = build_cpu_reference(args.model)
+    per_step = REF_BATCH if args.model != "large" else 1
     for i in range(args.warmup):
-        cpu_reference_step(model, cfg, per_step, i, store)
+        step(per_step, i)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        cpu_reference_step(model, cfg, per_step, 1000 + i, store)
+        step(per_step, 1000 + i)
     dt = time.perf_counter() - t0
     v = per_step * args.steps / dt
-    sample = f"{per_step} sample per step (577 image + 40 text tokens, {192 if args.model == 'large' else 96} fp64 Grams), VLMo-{args.model} all_moe, host cores only"
+    sample = (f"{per_step} samples per step (577 image + 40 text tokens each, {len(store)} fp64 Grams), VLMo-{args.model} all_moe, "
+              f"host cores only; {'UNMODIFIED reference sources through oracle/ref_shims' if kind == 'reference' else 'port: stock-torch mirror of the forward + the reference hook restated in oracle/ (reference sources absent on this box)'}")
     out = {
         "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (same generator as the GPU arm)",
-        "config": {"workload": f"RegMean Gram caching, VLMo-{args.model} all_moe, reference CPU path (stock forward + hook_gram_input "
-                               "restated from src/cache_gram_matrices.py:246-254), bounded sample", "global_batch": per_step,
+        "config": {"workload": f"RegMean Gram caching, VLMo-{args.model} all_moe, reference CPU path (stock forward + hook_gram_input, "
+                               "src/cache_gram_matrices.py:246-254), bounded sample", "global_batch": per_step,
                    "parallelism": "host threads"},
-        "cpu_baseline": {"value": round(v, 4), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+        "cpu_baseline": {"value": round(v, 4), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind,
                          "sample": sample, "cpu_model": cpu_model_name()},
         "e2e": {"value": round(v, 4), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -794,6 +1085,8 @@ def main():
                     help="also time Gram caching on the fused vision-language route (model.infer, type_id 2: row-sliced activations)")
     ap.add_argument("--irtr", action="store_true",
                     help="also run config 4: modality-arithmetic merge + IRTR forward over 5k synthetic images x 25k captions")
+    ap.add_argument("--no-vitl", action="store_true", help="skip the ViT-L leg (config 5) of the default line")
+    ap.add_argument("--no-irtr", action="store_true", help="skip the modality-arithmetic + 5k x 25k IRTR leg (config 4) of the default line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip timing the reference's fp64 hook with the model on the GPU")
     ap.add_argument("--profile", action="store_true",

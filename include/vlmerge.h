@@ -195,6 +195,12 @@ int vlm_spd_solve_right(double* s, int in_f, int64_t lds, double* r, int out_f, 
 int vlm_spd_solve_right_async(double* s, int in_f, int64_t lds, double* r, int out_f, int64_t ldr,
                               int* info_dev, void* stream);
 
+/* Pivoted-LU variant for a summed Gram that Cholesky rejects (VLM_ERR_NOT_SPD / potrf status > 0): the reference
+ * inverts with torch.inverse (LU; src/vilt/modules/vilt_module.py:432,483), which succeeds on any numerically
+ * non-singular matrix.  s must hold the FULL symmetric matrix again (potrf overwrote a triangle); both s and r are
+ * overwritten.  Synchronises `stream`.  VLM_ERR_NOT_SPD here means an exactly zero pivot (singular). */
+int vlm_lu_solve_right(double* s, int in_f, int64_t lds, double* r, int out_f, int64_t ldr, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -220,10 +220,24 @@ def irtr_recall(img_feats, txt_feats, iids, tiids):
     Returns (scores, (ir_r1, ir_r5, ir_r10, tr_r1, tr_r5, tr_r10))."""
     scores = np.asarray(img_feats) @ np.asarray(txt_feats).T
     iids, tiids = np.asarray(iids), np.asarray(tiids)
+
+    def top10(mat):
+        """Indices of the 10 largest entries of every row, best first (ties: lower index first, like a stable
+        descending sort) — a partition first, so the 5,000 x 25,000 COCO-sized matrix does not need six full sorts."""
+        k = min(10, mat.shape[1])
+        if mat.shape[1] > 64:
+            cand = np.argpartition(-mat, k - 1, axis=1)[:, :k]
+        else:
+            cand = np.broadcast_to(np.arange(mat.shape[1]), mat.shape).copy()
+        vals = np.take_along_axis(mat, cand, axis=1)
+        order = np.lexsort((cand, -vals), axis=1)
+        return np.take_along_axis(cand, order, axis=1)[:, :k]
+
+    by_image, by_caption = top10(scores), top10(scores.T)
     res = {}
     for k in (1, 5, 10):
-        top = np.argsort(-scores, axis=1, kind="stable")[:, :k]           # per image: best captions (:688-690)
+        top = by_image[:, :k]                                              # per image: best captions (:688-690)
         res[f"tr_r{k}"] = (iids[:, None] == tiids[top]).max(axis=1).astype(np.float32).mean()
-        top = np.argsort(-scores, axis=0, kind="stable")[:k, :]           # per caption: best images (:699-701)
+        top = by_caption[:, :k].T                                          # per caption: best images (:699-701)
         res[f"ir_r{k}"] = (tiids[None, :] == iids[top]).max(axis=0).astype(np.float32).mean()
     return scores, (res["ir_r1"], res["ir_r5"], res["ir_r10"], res["tr_r1"], res["tr_r5"], res["tr_r10"])

@@ -86,6 +86,66 @@ def test_singular_gram_sum_raises_like_torch_inverse():
         vlm.regmean(_t(sd), cfg, gram_matrices=_t(bad))
 
 
+def test_cholesky_rejected_sum_is_solved_by_lu_like_torch_inverse():
+    """The reference inverts the summed Gram with torch.inverse (LU, vilt_module.py:432,483): it returns a result for
+    any numerically non-singular matrix.  A sum that is symmetric but NOT positive definite (one negative
+    eigenvalue — what rounding can do to an ill-conditioned Gram sum) makes potrf fail; regmean then solves that
+    problem with pivoted LU, warns, and still matches the oracle's explicit inverse."""
+    sd, cfg, grams = G.inputs("regmean_s1.0")
+    rng = np.random.default_rng(5)
+    bad = dict(grams)
+    hit = [k for k in bad if k.startswith("transformer.blocks.1.") and k.endswith(".proj")]
+    assert hit
+    d = bad[hit[0]].shape[0]
+    q, _ = np.linalg.qr(rng.standard_normal((d, d)))          # same eigenvectors for both experts
+    for k in hit:
+        lam = np.linspace(1.0, 3.0, d)
+        lam[d // 2] = -0.75 if k.endswith("attn.v.proj") else 0.25     # the SUM keeps one negative eigen-direction
+        bad[k] = (q * lam) @ q.T
+        bad[k] = (bad[k] + bad[k].T) / 2
+    want = oracle.regmean(sd, bad, cfg)
+    for streams in (1, 4):
+        stats = {}
+        with pytest.warns(RuntimeWarning, match="not positive definite"):
+            got = vlm.regmean(_t(sd, "cuda"), cfg, gram_matrices=_t(bad, "cuda"), solve_streams=streams, stats=stats)
+        assert stats["lu_fallbacks"] == 1
+        for k, w in want.items():
+            if "transformer.blocks." in k and "gamma" not in k:
+                g = got[k].cpu().numpy()
+                assert np.linalg.norm(g - w) <= 1e-9 * max(np.linalg.norm(w), 1e-30), k
+
+
+@pytest.mark.parametrize("device_inputs", [False, True], ids=["host-inputs", "device-inputs"])
+def test_load_time_dispatch_all_three_branches(device_inputs, tmp_path):
+    """vilt_module.py:284-291: `merge_weights` / `sum_task_vectors` / `regmean` config switches select the method;
+    Merger.apply is that dispatch on the CUDA path, checked against the reference goldens for each branch."""
+    dev = "cuda" if device_inputs else "cpu"
+    torch.save({"state_dict": _t(G.central)}, tmp_path / "central.pth")
+    for vname, switch in (("interp_a0.5", "merge_weights"), ("arith_l0.75", "sum_task_vectors"), ("regmean_s0.9", "regmean")):
+        sd, cfg, grams = G.inputs(vname)
+        assert G.variants[vname]["method"] == switch
+        extra = {switch: True}
+        if switch == "sum_task_vectors":
+            extra["central_weight"] = str(tmp_path / "central.pth")
+        if switch == "regmean":
+            from collections import defaultdict
+            gd = defaultdict(float)
+            gd.update(_t(grams))
+            torch.save(gd, tmp_path / "grams.pth")
+            extra["gram_matrices"] = str(tmp_path / "grams.pth")
+        got = vlm.Merger(dict(cfg, **extra)).apply(_t(sd, dev))
+        assert list(got.keys()) == G.variants[vname]["keys"]
+        for k, w in G.expected(vname).items():
+            g = got[k].cpu().numpy()
+            if w.dtype == np.float32:
+                assert np.array_equal(g, w), (vname, k)
+            else:
+                assert np.linalg.norm(g - w) / np.linalg.norm(w) < 1e-9, (vname, k)
+    sd, cfg, _ = G.inputs("interp_a0.5")
+    tsd = _t(sd, dev)
+    assert vlm.Merger(dict(cfg)).apply(tsd) is tsd          # no switch set: the checkpoint is loaded as it is
+
+
 @pytest.mark.parametrize("device_inputs", [False, True], ids=["host-inputs", "device-inputs"])
 def test_regmean_concurrent_streams_equal_sequential(device_inputs):
     """The per-linear problems spread over several streams (default) vs one after the other: same kernels on the

@@ -214,6 +214,9 @@ struct Cusolver {
   cusolverStatus_t (*potrf_bufsize)(cusolverDnHandle_t, int, int, double*, int, int*) = nullptr;
   cusolverStatus_t (*potrf)(cusolverDnHandle_t, int, int, double*, int, double*, int, int*) = nullptr;
   cusolverStatus_t (*potrs)(cusolverDnHandle_t, int, int, int, const double*, int, double*, int, int*) = nullptr;
+  cusolverStatus_t (*getrf_bufsize)(cusolverDnHandle_t, int, int, double*, int, int*) = nullptr;
+  cusolverStatus_t (*getrf)(cusolverDnHandle_t, int, int, double*, int, double*, int*, int*) = nullptr;
+  cusolverStatus_t (*getrs)(cusolverDnHandle_t, int, int, int, const double*, int, const int*, double*, int, int*) = nullptr;
 };
 Cusolver g_cs;
 std::mutex g_cs_mu;
@@ -235,6 +238,9 @@ int load_cusolver() {
   VLM_SYM(potrf_bufsize, "cusolverDnDpotrf_bufferSize");
   VLM_SYM(potrf, "cusolverDnDpotrf");
   VLM_SYM(potrs, "cusolverDnDpotrs");
+  VLM_SYM(getrf_bufsize, "cusolverDnDgetrf_bufferSize");
+  VLM_SYM(getrf, "cusolverDnDgetrf");
+  VLM_SYM(getrs, "cusolverDnDgetrs");
 #undef VLM_SYM
   return 0;
 }
@@ -250,7 +256,9 @@ extern "C" int vlm_gram_scale_accum(const void* g, int g_dtype, int d, int64_t l
   VLM_REQUIRE(g_dtype == VLM_F64 || g_dtype == VLM_F32, VLM_ERR_INVALID_ARG,
               "vlm_gram_scale_accum: g_dtype must be VLM_F64 or VLM_F32");
   const int64_t n = (int64_t)d * d;
-  const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  int nsm = 0;
+  if (int rc = device_sm_count(&nsm)) return rc;
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)nsm * 8);
   auto s = static_cast<cudaStream_t>(stream);
   if (g_dtype == VLM_F64)
     gram_scale_accum_kernel<double>
@@ -304,47 +312,98 @@ extern "C" int vlm_regmean_rhs(const float* w, int out_f, int in_f, int64_t ldw,
 }
 
 namespace {
-// One cuSOLVER handle per (device, stream): a handle owns a cuBLAS handle and workspace, so concurrent solves on
-// different streams must not share one.
-std::map<std::pair<int, cudaStream_t>, cusolverDnHandle_t> g_cs_handles;
+// One solver context per (device, stream): a cuSOLVER handle owns a cuBLAS handle and workspace, so concurrent solves
+// on different streams must not share one; the factorisation workspace is kept with it and only ever grows (a
+// stream-ordered cudaMallocAsync per solve went back to the driver at every synchronisation: milliseconds of
+// jitter per call, BENCH_r01 regmean.seconds_both_runs 0.066 / 0.288).  The library assumes one host thread per
+// device drives these entry points at a time (the lock covers the map, not the use of a context).
+struct SolveCtx {
+  cusolverDnHandle_t h = nullptr;
+  double* work = nullptr;
+  size_t work_elems = 0;
+};
+std::map<std::pair<int, cudaStream_t>, SolveCtx> g_cs_ctx;
 
-// potrf + potrs on `st`; info_dev[0..1] receive the two LAPACK-style status words.  `work_out` (stream-ordered
-// allocation) is returned for the caller to free after the solve has been enqueued.
-int enqueue_spd_solve(double* s, int in_f, int64_t lds, double* r, int out_f, int64_t ldr, int* info_dev,
-                      cudaStream_t st) {
+int solve_ctx(cudaStream_t st, size_t want_elems, SolveCtx* out) {
   int dev = 0;
   VLM_CUDA(cudaGetDevice(&dev));
-  cusolverDnHandle_t h = nullptr;
-  {
-    std::lock_guard<std::mutex> lk(g_cs_mu);
-    if (int rc = load_cusolver()) return rc;
-    auto key = std::make_pair(dev, st);
-    auto it = g_cs_handles.find(key);
-    if (it == g_cs_handles.end()) {
-      VLM_REQUIRE(g_cs_handles.size() < 256, VLM_ERR_UNSUPPORTED, "too many distinct streams use vlm_spd_solve_right");
-      VLM_REQUIRE(g_cs.create(&h) == 0, VLM_ERR_DRIVER, "cusolverDnCreate failed");
-      VLM_REQUIRE(g_cs.set_stream(h, st) == 0, VLM_ERR_DRIVER, "cusolverDnSetStream failed");
-      g_cs_handles.emplace(key, h);
-    } else {
-      h = it->second;
-    }
+  std::lock_guard<std::mutex> lk(g_cs_mu);
+  if (int rc = load_cusolver()) return rc;
+  auto key = std::make_pair(dev, st);
+  auto it = g_cs_ctx.find(key);
+  if (it == g_cs_ctx.end()) {
+    VLM_REQUIRE(g_cs_ctx.size() < 256, VLM_ERR_UNSUPPORTED, "too many distinct streams use vlm_spd_solve_right");
+    SolveCtx c;
+    VLM_REQUIRE(g_cs.create(&c.h) == 0, VLM_ERR_DRIVER, "cusolverDnCreate failed");
+    VLM_REQUIRE(g_cs.set_stream(c.h, st) == 0, VLM_ERR_DRIVER, "cusolverDnSetStream failed");
+    it = g_cs_ctx.emplace(key, c).first;
   }
+  SolveCtx& c = it->second;
+  if (c.work_elems < want_elems) {
+    // the old buffer may still be in use by work queued on `st`: free it in stream order, allocate the new one now
+    if (c.work) VLM_CUDA(cudaFreeAsync(c.work, st));
+    c.work = nullptr;
+    c.work_elems = 0;
+    const size_t n = std::max<size_t>(want_elems, (size_t)1 << 16);
+    VLM_CUDA(cudaMalloc(reinterpret_cast<void**>(&c.work), sizeof(double) * n));
+    c.work_elems = n;
+  }
+  *out = c;
+  return 0;
+}
+
+// potrf + potrs on `st`; info_dev[0..1] receive the two LAPACK-style status words.
+int enqueue_spd_solve(double* s, int in_f, int64_t lds, double* r, int out_f, int64_t ldr, int* info_dev,
+                      cudaStream_t st) {
+  SolveCtx c;
+  if (int rc = solve_ctx(st, 0, &c)) return rc;
   // Row-major symmetric S is also column-major S.  Row-major R (out_f x in_f) read column-major is
   // R^T (in_f x out_f), and S * X^T = R^T  <=>  X = R * S^{-1}: potrs leaves X row-major in r.
   const int uplo_lower = 0;  // CUBLAS_FILL_MODE_LOWER
   int lwork = 0;
-  VLM_REQUIRE(g_cs.potrf_bufsize(h, uplo_lower, in_f, s, (int)lds, &lwork) == 0, VLM_ERR_DRIVER,
+  VLM_REQUIRE(g_cs.potrf_bufsize(c.h, uplo_lower, in_f, s, (int)lds, &lwork) == 0, VLM_ERR_DRIVER,
               "cusolverDnDpotrf_bufferSize failed");
-  double* work = nullptr;
-  VLM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&work), sizeof(double) * (size_t)std::max(lwork, 1), st));
-  cusolverStatus_t cs1 = g_cs.potrf(h, uplo_lower, in_f, s, (int)lds, work, lwork, info_dev);
-  cusolverStatus_t cs2 = g_cs.potrs(h, uplo_lower, in_f, out_f, s, (int)lds, r, (int)ldr, info_dev + 1);
+  if (int rc = solve_ctx(st, (size_t)std::max(lwork, 1), &c)) return rc;
+  cusolverStatus_t cs1 = g_cs.potrf(c.h, uplo_lower, in_f, s, (int)lds, c.work, lwork, info_dev);
+  cusolverStatus_t cs2 = g_cs.potrs(c.h, uplo_lower, in_f, out_f, s, (int)lds, r, (int)ldr, info_dev + 1);
   count_launch(2);
-  cudaFreeAsync(work, st);
   VLM_REQUIRE(cs1 == 0 && cs2 == 0, VLM_ERR_INTERNAL, "cuSOLVER potrf/potrs status %d/%d", cs1, cs2);
   return 0;
 }
 }  // namespace
+
+// General (pivoted LU) variant of vlm_spd_solve_right for a summed Gram that Cholesky rejects: the reference
+// inverts with torch.inverse (LU, src/vilt/modules/vilt_module.py:432,483), which returns a result for any
+// numerically non-singular matrix — e.g. a Gram sum that rounding has left slightly indefinite.  Rare path:
+// allocates its pivots and synchronises `stream`.
+extern "C" int vlm_lu_solve_right(double* s, int in_f, int64_t lds, double* r, int out_f, int64_t ldr, void* stream) {
+  VLM_REQUIRE(s && r && in_f > 0 && out_f > 0 && lds >= in_f && ldr >= in_f, VLM_ERR_INVALID_ARG,
+              "vlm_lu_solve_right: bad arguments");
+  auto st = static_cast<cudaStream_t>(stream);
+  SolveCtx c;
+  if (int rc = solve_ctx(st, 0, &c)) return rc;
+  int lwork = 0;
+  VLM_REQUIRE(g_cs.getrf_bufsize(c.h, in_f, in_f, s, (int)lds, &lwork) == 0, VLM_ERR_DRIVER,
+              "cusolverDnDgetrf_bufferSize failed");
+  if (int rc = solve_ctx(st, (size_t)std::max(lwork, 1), &c)) return rc;
+  int* ipiv = nullptr;
+  VLM_CUDA(cudaMalloc(reinterpret_cast<void**>(&ipiv), sizeof(int) * ((size_t)in_f + 2)));
+  int* info = ipiv + in_f;
+  // S symmetric: its row-major storage is also its column-major storage; S * X^T = R^T as in the Cholesky path
+  cusolverStatus_t cs1 = g_cs.getrf(c.h, in_f, in_f, s, (int)lds, c.work, ipiv, info);
+  cusolverStatus_t cs2 = g_cs.getrs(c.h, 0 /* CUBLAS_OP_N */, in_f, out_f, s, (int)lds, ipiv, r, (int)ldr, info + 1);
+  count_launch(2);
+  int info_host[2] = {0, 0};
+  cudaError_t e = cudaMemcpyAsync(info_host, info, sizeof(info_host), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(ipiv);
+  if (e != cudaSuccess) return fail((int)e, "vlm_lu_solve_right: %s", cudaGetErrorString(e));
+  VLM_REQUIRE(cs1 == 0 && cs2 == 0, VLM_ERR_INTERNAL, "cuSOLVER getrf/getrs status %d/%d", cs1, cs2);
+  VLM_REQUIRE(info_host[0] == 0, VLM_ERR_NOT_SPD, "summed Gram is singular (zero pivot %d in the LU factorisation)",
+              info_host[0]);
+  VLM_REQUIRE(info_host[1] == 0, VLM_ERR_INTERNAL, "cusolverDnDgetrs info %d", info_host[1]);
+  return 0;
+}
 
 extern "C" int vlm_spd_solve_right_async(double* s, int in_f, int64_t lds, double* r, int out_f, int64_t ldr,
                                          int* info_dev, void* stream) {
@@ -359,7 +418,7 @@ extern "C" int vlm_spd_solve_right(double* s, int in_f, int64_t lds, double* r, 
               "vlm_spd_solve_right: bad arguments");
   auto st = static_cast<cudaStream_t>(stream);
   int* info = nullptr;
-  VLM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&info), sizeof(int) * 2, st));
+  VLM_CUDA(cudaMalloc(reinterpret_cast<void**>(&info), sizeof(int) * 2));
   const int rc = enqueue_spd_solve(s, in_f, lds, r, out_f, ldr, info, st);
   int info_host[2] = {0, 0};
   cudaError_t e = cudaSuccess;
@@ -367,7 +426,7 @@ extern "C" int vlm_spd_solve_right(double* s, int in_f, int64_t lds, double* r, 
     e = cudaMemcpyAsync(info_host, info, sizeof(info_host), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   }
-  cudaFreeAsync(info, st);
+  cudaFree(info);
   if (rc != 0) return rc;
   if (e != cudaSuccess) return fail((int)e, "vlm_spd_solve_right: %s", cudaGetErrorString(e));
   VLM_REQUIRE(info_host[0] == 0, VLM_ERR_NOT_SPD,

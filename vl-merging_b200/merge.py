@@ -13,7 +13,6 @@ GPU inputs are used in place and the result stays on the GPU.  With a process gr
 sharded by tensor over the ranks and the merged tensors are all-gathered at the end.
 """
 import ctypes
-import time
 from types import SimpleNamespace
 
 import torch
@@ -44,6 +43,14 @@ def _resolve_device(state_dict, device):
             return v.device
     if not torch.cuda.is_available():
         raise RuntimeError("the merge hot path runs on a CUDA device only (no CPU fallback)")
+    # host checkpoint and no device given.  Under a one-process-per-GPU launcher (torchrun / Lightning DDP) the
+    # merges are called from the model constructor, BEFORE the trainer calls set_device: follow LOCAL_RANK there,
+    # so that N ranks do not all stage their arenas on cuda:0.
+    import os
+
+    local = os.environ.get("LOCAL_RANK")
+    if local is not None and local.isdigit() and int(local) < torch.cuda.device_count():
+        return torch.device("cuda", int(local))
     return torch.device("cuda", torch.cuda.current_device())
 
 
@@ -227,7 +234,14 @@ def _assemble(state_dict, ops, computed):
     return new
 
 
-def _out_device(state_dict, ops):
+def _out_device(state_dict, ops, override=None, device=None):
+    """Where the merged tensors go: where the inputs live (the reference's behaviour: CPU in, CPU out), unless the
+    caller says otherwise.  Under a process group the gathered result is on every rank's GPU anyway; copying it to
+    the host on EVERY rank is N device->host copies into the same host memory, so a launcher that only needs the
+    host copy once passes out_device="cpu" on rank 0 and "cuda" elsewhere."""
+    if override is not None:
+        override = torch.device(override)
+        return device if override.type == "cuda" else override
     for op in ops:
         for k in op.srcs:
             return state_dict[k].device
@@ -236,20 +250,22 @@ def _out_device(state_dict, ops):
     return torch.device("cpu")
 
 
-def merge_weights(state_dict, config, device=None, num_layers=12, group=None, stats=None):
+def merge_weights(state_dict, config, device=None, num_layers=12, group=None, stats=None, out_device=None):
     """Interpolation merge.  config keys: merge_ratio, only_activate_used_experts,
-    vlffn_start_layer_index, loss_names (src/vilt/config.py:141-149)."""
+    vlffn_start_layer_index, loss_names (src/vilt/config.py:141-149).
+    out_device: None = where the inputs live; "cuda" = leave the merged tensors on the merge device; "cpu"."""
     device = _resolve_device(state_dict, device)
     ops = plan_merge_weights(state_dict.keys(), config, num_layers)
     todo = [op for op in ops if not op.passthrough]
     shapes = {op.dst: state_dict[op.srcs[0]].shape for op in todo}
     with torch.cuda.device(device):
         computed = _run_elementwise(todo, lambda op, j: state_dict[op.srcs[j]], shapes, device,
-                                    _out_device(state_dict, todo), group, stats)
+                                    _out_device(state_dict, todo, out_device, device), group, stats)
     return _assemble(state_dict, ops, computed)
 
 
-def sum_task_vectors(state_dict, config, device=None, num_layers=12, group=None, stats=None, central_weight=None):
+def sum_task_vectors(state_dict, config, device=None, num_layers=12, group=None, stats=None, central_weight=None,
+                     out_device=None):
     """Modality arithmetic with the reference's sequential semantics.  The centre is
     config['central_weight'] (a checkpoint path, as in the reference) unless a dict is passed.  Unlike the
     reference, the loaded centre is not mutated."""
@@ -265,65 +281,145 @@ def sum_task_vectors(state_dict, config, device=None, num_layers=12, group=None,
         return central[op.dst] if j == 0 else state_dict[op.srcs[j - 1]]
 
     with torch.cuda.device(device):
-        computed = _run_elementwise(todo, lookup, shapes, device, _out_device(state_dict, todo), group, stats)
+        computed = _run_elementwise(todo, lookup, shapes, device, _out_device(state_dict, todo, out_device, device),
+                                    group, stats)
     return _assemble(state_dict, ops, computed)
 
 
-_SOLVE_STREAMS = {}   # device -> side streams of the concurrent RegMean path (libvlmerge keeps one cuSOLVER handle per stream)
+_SOLVE_STREAMS = {}   # device -> side streams of the concurrent RegMean path (libvlmerge keeps one solver context per stream)
+_SUM_WORKSPACE = {}   # device -> flat fp64 workspace for the summed Grams, kept across calls (it only ever grows)
 
 
-def _regmean_linears_concurrent(lib, state_dict, grams, lin_ops, mine, cost, alpha, device, n_streams, results):
-    """The linear problems `mine` of regmean() on n_streams CUDA streams (largest first, each to the least
-    loaded stream): per problem vlm_gram_scale_accum + vlm_regmean_rhs per expert, then vlm_spd_solve_right_async.
-    One status read at the end; raises like the sequential path."""
+def _workspace(device, numel):
+    ws = _SUM_WORKSPACE.get(device)
+    if ws is None or ws.numel() < numel:
+        _SUM_WORKSPACE[device] = None
+        ws = _SUM_WORKSPACE[device] = torch.empty(int(numel), dtype=torch.float64, device=device)
+    return ws
+
+
+def _regmean_linears(lib, state_dict, grams, lin_ops, mine, cost, alpha, device, n_streams, results, stats=None):
+    """The linear problems `mine` of regmean(): per problem vlm_gram_scale_accum + vlm_regmean_rhs per expert, then
+    vlm_spd_solve_right_async, on n_streams CUDA streams (largest problem first, each to the least loaded stream;
+    n_streams = 1: everything on the caller's stream, and `stats` receives the RHS / solve split from CUDA events).
+    Every buffer is carved out BEFORE the streams fork — one fresh fp64 arena for the results (the returned tensors
+    are views of it), one cached workspace for the summed Grams, operands staged on the caller's stream — so no
+    allocation happens inside a side-stream context and a repeated call does the same work in the same time.
+    One status read at the end.  A summed Gram that Cholesky rejects is solved again by pivoted LU
+    (vlm_lu_solve_right), like the reference's torch.inverse (vilt_module.py:432,483); an exactly singular one
+    raises LinAlgError as torch.inverse does."""
+    import warnings
+
     cur = torch.cuda.current_stream(device)
-    pool = _SOLVE_STREAMS.setdefault(device, [])
-    while len(pool) < n_streams:
-        pool.append(torch.cuda.Stream(device))
-    streams = pool[:n_streams]
+    shapes = {idx: tuple(state_dict[lin_ops[idx].regmean[0][0]].shape) for idx in mine}
+    acc_all = torch.empty(sum(o * i for o, i in shapes.values()), dtype=torch.float64, device=device)
+    ws = _workspace(device, sum(i * i for _, i in shapes.values()))
+    acc, summed = {}, {}
+    a_off = s_off = 0
+    for idx in mine:
+        o, i = shapes[idx]
+        acc[idx] = acc_all[a_off: a_off + o * i].view(o, i)
+        summed[idx] = ws[s_off: s_off + i * i].view(i, i)
+        a_off += o * i
+        s_off += i * i
+    # operands: used in place when resident (fp32 weights; fp32 or fp64 Grams), staged here otherwise
+    staged = {}
+
+    def operand(t, gram):
+        key = (id(t), gram)
+        if key not in staged:
+            v = t.detach()
+            if gram:
+                if v.dtype not in (torch.float64, torch.float32):
+                    v = v.double()
+                v = v.to(device=device, non_blocking=True)
+            else:
+                v = v.to(device=device, dtype=torch.float32, non_blocking=True)
+            staged[key] = v if v.stride(-1) == 1 and v.dim() == 2 else v.contiguous()
+        return staged[key]
+
+    for idx in mine:
+        for wkey, gkey in lin_ops[idx].regmean:
+            g = operand(grams[gkey], True)
+            if tuple(g.shape) != (shapes[idx][1], shapes[idx][1]):
+                raise RuntimeError(f"Gram {gkey} has shape {tuple(g.shape)}, expected {(shapes[idx][1],) * 2}")
+            operand(state_dict[wkey], False)
     info = torch.zeros(len(lin_ops), 2, dtype=torch.int32, device=device)
-    for st in streams:
-        st.wait_stream(cur)
-    load = [0] * n_streams
-    for idx in sorted(mine, key=lambda i: (-cost(lin_ops[i]), i)):
-        op = lin_ops[idx]
-        k = min(range(n_streams), key=lambda j: (load[j], j))
-        load[k] += cost(op)
-        st = streams[k]
-        out_f, in_f = state_dict[op.regmean[0][0]].shape
-        with torch.cuda.stream(st):
-            acc = torch.empty(out_f, in_f, dtype=torch.float64, device=device)
-            summed = torch.empty(in_f, in_f, dtype=torch.float64, device=device)
-            for n, (wkey, gkey) in enumerate(op.regmean):
-                w = state_dict[wkey].detach().to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
-                g = grams[gkey]
-                if g.dtype not in (torch.float64, torch.float32):
-                    g = g.double()
-                g = g.detach().to(device=device, non_blocking=True).contiguous()
-                if tuple(g.shape) != (in_f, in_f):
-                    raise RuntimeError(f"Gram {gkey} has shape {tuple(g.shape)}, expected {(in_f, in_f)}")
-                gdt = _lib.VLM_F64 if g.dtype == torch.float64 else _lib.VLM_F32
-                _lib.check(lib.vlm_gram_scale_accum(g.data_ptr(), gdt, in_f, g.stride(0), alpha, summed.data_ptr(),
-                                                    summed.stride(0), int(n > 0), st.cuda_stream))
-                _lib.check(lib.vlm_regmean_rhs(w.data_ptr(), out_f, in_f, w.stride(0), g.data_ptr(), gdt, g.stride(0),
-                                               alpha, acc.data_ptr(), acc.stride(0), int(n > 0), st.cuda_stream))
-                w.record_stream(st)      # inputs that live on another stream's pool must outlive this launch
-                g.record_stream(st)
-            _lib.check(lib.vlm_spd_solve_right_async(summed.data_ptr(), in_f, summed.stride(0), acc.data_ptr(), out_f,
-                                                     acc.stride(0), info[idx].data_ptr(), st.cuda_stream))
-            acc.record_stream(cur)       # consumed on the caller's stream after the join below
-        results[op.dst] = acc
-    for st in streams:
-        cur.wait_stream(st)
+
+    def enqueue_rhs(idx, st):
+        out_f, in_f = shapes[idx]
+        for n, (wkey, gkey) in enumerate(lin_ops[idx].regmean):
+            w, g = operand(state_dict[wkey], False), operand(grams[gkey], True)
+            gdt = _lib.VLM_F64 if g.dtype == torch.float64 else _lib.VLM_F32
+            _lib.check(lib.vlm_gram_scale_accum(g.data_ptr(), gdt, in_f, g.stride(0), alpha, summed[idx].data_ptr(),
+                                                summed[idx].stride(0), int(n > 0), st))
+            _lib.check(lib.vlm_regmean_rhs(w.data_ptr(), out_f, in_f, w.stride(0), g.data_ptr(), gdt, g.stride(0),
+                                           alpha, acc[idx].data_ptr(), acc[idx].stride(0), int(n > 0), st))
+
+    def enqueue_solve(idx, st):
+        out_f, in_f = shapes[idx]
+        _lib.check(lib.vlm_spd_solve_right_async(summed[idx].data_ptr(), in_f, summed[idx].stride(0), acc[idx].data_ptr(),
+                                                 out_f, acc[idx].stride(0), info[idx].data_ptr(), st))
+
+    order = sorted(mine, key=lambda i: (-cost(lin_ops[i]), i))
+    n_streams = max(1, min(int(n_streams), len(mine)))
+    events = []
+    if n_streams == 1:
+        st = cur.cuda_stream
+        for idx in order:
+            if stats is not None:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                ev[0].record(cur)
+            enqueue_rhs(idx, st)
+            if stats is not None:
+                ev[1].record(cur)
+            enqueue_solve(idx, st)
+            if stats is not None:
+                ev[2].record(cur)
+                events.append(ev)
+    else:
+        pool = _SOLVE_STREAMS.setdefault(device, [])
+        while len(pool) < n_streams:
+            pool.append(torch.cuda.Stream(device))
+        streams = pool[:n_streams]
+        for st in streams:
+            st.wait_stream(cur)
+        load = [0] * n_streams
+        for idx in order:
+            k = min(range(n_streams), key=lambda j: (load[j], j))
+            load[k] += cost(lin_ops[idx])
+            enqueue_rhs(idx, streams[k].cuda_stream)
+            enqueue_solve(idx, streams[k].cuda_stream)
+        for st in streams:
+            cur.wait_stream(st)
     status = info.cpu()                  # synchronises the caller's stream, hence all of the above
+    if stats is not None:
+        stats["solve_streams"] = n_streams
+        if events:
+            stats["rhs_seconds"] = stats.get("rhs_seconds", 0.0) + sum(e[0].elapsed_time(e[1]) for e in events) * 1e-3
+            stats["solve_seconds"] = stats.get("solve_seconds", 0.0) + sum(e[1].elapsed_time(e[2]) for e in events) * 1e-3
     for idx in mine:
         potrf, potrs = int(status[idx, 0]), int(status[idx, 1])
-        if potrf != 0:                   # the reference's torch.inverse raises on a singular sum too
-            raise torch.linalg.LinAlgError(
-                f"{lin_ops[idx].dst}: summed Gram is not positive definite (leading minor {potrf}); calibrate with "
-                "more rows than features or use scaling_for_non_diag < 1")
-        if potrs != 0:
+        if potrf != 0:
+            # Cholesky rejected the sum (not numerically positive definite): redo this problem with pivoted LU
+            warnings.warn(f"{lin_ops[idx].dst}: summed Gram is not positive definite (leading minor {potrf}); "
+                          "solving with pivoted LU like torch.inverse — calibrate with more rows than features or use "
+                          "scaling_for_non_diag < 1", RuntimeWarning, stacklevel=3)
+            enqueue_rhs(idx, cur.cuda_stream)
+            out_f, in_f = shapes[idx]
+            try:
+                _lib.check(lib.vlm_lu_solve_right(summed[idx].data_ptr(), in_f, summed[idx].stride(0), acc[idx].data_ptr(),
+                                                  out_f, acc[idx].stride(0), cur.cuda_stream))
+            except _lib.VlmError as e:
+                if e.code == _lib.ERR_NOT_SPD:  # the reference's torch.inverse raises on a singular sum too
+                    raise torch.linalg.LinAlgError(f"{lin_ops[idx].dst}: {e}") from e
+                raise
+            if stats is not None:
+                stats["lu_fallbacks"] = stats.get("lu_fallbacks", 0) + 1
+        elif potrs != 0:
             raise RuntimeError(f"{lin_ops[idx].dst}: cusolverDnDpotrs info {potrs}")
+    for idx in mine:
+        results[lin_ops[idx].dst] = acc[idx]
 
 
 def _as_gram_dict(grams):
@@ -334,7 +430,7 @@ def _as_gram_dict(grams):
 
 
 def regmean(state_dict, config, device=None, num_layers=12, group=None, stats=None, gram_matrices=None,
-            solve_streams=8):
+            solve_streams=8, out_device=None):
     """RegMean merge.  config keys: gram_matrices (path of the Gram file, as in the reference — or pass
     gram_matrices= a dict / GramCache), scaling_for_non_diag, vlffn_start_layer_index, loss_names.
     Linear weights come back fp64 like the reference's; biases / LayerNorms fp32.
@@ -355,7 +451,7 @@ def regmean(state_dict, config, device=None, num_layers=12, group=None, stats=No
     todo = [op for op in ops if not op.passthrough]
     mean_ops = [op for op in todo if op.regmean is None]
     lin_ops = [op for op in todo if op.regmean is not None]
-    out_device = _out_device(state_dict, todo)
+    out_device = _out_device(state_dict, todo, out_device, device)
     with torch.cuda.device(device):
         shapes = {op.dst: state_dict[op.srcs[0]].shape for op in mean_ops}
         computed = _run_elementwise(mean_ops, lambda op, j: state_dict[op.srcs[j]], shapes, device, out_device,
@@ -371,53 +467,10 @@ def regmean(state_dict, config, device=None, num_layers=12, group=None, stats=No
         lin_sizes = [int(state_dict[op.regmean[0][0]].numel()) for op in lin_ops]
         lin_layout = ShardLayout(lin_sizes, world, cost=lambda i: cost(lin_ops[i]), align=1)
         owner = lin_layout.owner
-        stream = torch.cuda.current_stream(device).cuda_stream
         results = {}
-        t_rhs = t_solve = 0.0
         mine_lin = [idx for idx in range(len(lin_ops)) if owner[idx] == rank]
-        concurrent = solve_streams > 1 and len(mine_lin) > 1
-        if concurrent:
-            _regmean_linears_concurrent(lib, state_dict, grams, lin_ops, mine_lin, cost, alpha, device,
-                                        min(int(solve_streams), len(mine_lin)), results)
-            if stats is not None:
-                stats["solve_streams"] = min(int(solve_streams), len(mine_lin))
-        for idx, op in enumerate(lin_ops):
-            if owner[idx] != rank or concurrent:
-                continue
-            out_f, in_f = state_dict[op.regmean[0][0]].shape
-            acc = torch.empty(out_f, in_f, dtype=torch.float64, device=device)
-            summed = torch.empty(in_f, in_f, dtype=torch.float64, device=device)
-            t0 = time.perf_counter() if stats is not None else 0.0
-            for n, (wkey, gkey) in enumerate(op.regmean):
-                w = state_dict[wkey].detach().to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
-                g = grams[gkey]
-                if g.dtype not in (torch.float64, torch.float32):
-                    g = g.double()
-                g = g.detach().to(device=device, non_blocking=True).contiguous()
-                if tuple(g.shape) != (in_f, in_f):
-                    raise RuntimeError(f"Gram {gkey} has shape {tuple(g.shape)}, expected {(in_f, in_f)}")
-                gdt = _lib.VLM_F64 if g.dtype == torch.float64 else _lib.VLM_F32
-                _lib.check(lib.vlm_gram_scale_accum(g.data_ptr(), gdt, in_f, g.stride(0), alpha, summed.data_ptr(),
-                                                    summed.stride(0), int(n > 0), stream))
-                _lib.check(lib.vlm_regmean_rhs(w.data_ptr(), out_f, in_f, w.stride(0), g.data_ptr(), gdt, g.stride(0),
-                                               alpha, acc.data_ptr(), acc.stride(0), int(n > 0), stream))
-            if stats is not None:
-                torch.cuda.current_stream(device).synchronize()
-                t1 = time.perf_counter()
-                t_rhs += t1 - t0
-            try:
-                _lib.check(lib.vlm_spd_solve_right(summed.data_ptr(), in_f, summed.stride(0), acc.data_ptr(), out_f,
-                                                   acc.stride(0), stream))
-            except _lib.VlmError as e:
-                if e.code == _lib.ERR_NOT_SPD:  # the reference's torch.inverse raises on a singular sum too
-                    raise torch.linalg.LinAlgError(f"{op.dst}: {e}") from e
-                raise
-            if stats is not None:
-                t_solve += time.perf_counter() - t1
-            results[op.dst] = acc
-        if stats is not None:
-            stats["rhs_seconds"] = stats.get("rhs_seconds", 0.0) + t_rhs
-            stats["solve_seconds"] = stats.get("solve_seconds", 0.0) + t_solve
+        if mine_lin:
+            _regmean_linears(lib, state_dict, grams, lin_ops, mine_lin, cost, alpha, device, solve_streams, results, stats)
 
         if world > 1:  # all-gather the solved weights: flat fp64, every rank knows every size
             local = torch.zeros(lin_layout.width, dtype=torch.float64, device=device)
@@ -438,6 +491,8 @@ class Merger:
     style patching, or Merger(config).regmean(state_dict)."""
 
     def __init__(self, config, num_layers=12, device=None, group=None):
+        """device=None: the device the state_dict lives on, else cuda:LOCAL_RANK under a launcher, else the current
+        device (see _resolve_device)."""
         self.hparams = SimpleNamespace(config=config)
         self.num_layers, self.device, self.group = num_layers, device, group
 
@@ -462,4 +517,18 @@ class Merger:
         return state_dict
 
 
-__all__ = ["merge_weights", "sum_task_vectors", "regmean", "Merger", "WSUM", "SEQ_LERP", "MEAN"]
+def independent(state_dict):
+    """Merged tensors that come back on the CPU are views of ONE pinned host buffer (a single device->host copy):
+    keeping any of them alive keeps the whole buffer, and torch.save of a subset serialises the shared storage.  This
+    returns the same dict with every such view copied into its own ordinary tensor, like the reference's outputs."""
+    seen = {}
+    for v in state_dict.values():
+        if torch.is_tensor(v) and v.device.type == "cpu":
+            key = v.untyped_storage().data_ptr()
+            seen[key] = seen.get(key, 0) + 1
+    return {k: (v.clone() if torch.is_tensor(v) and v.device.type == "cpu" and
+                (seen.get(v.untyped_storage().data_ptr(), 0) > 1 or v.is_pinned()) else v)
+            for k, v in state_dict.items()}
+
+
+__all__ = ["merge_weights", "sum_task_vectors", "regmean", "Merger", "independent", "WSUM", "SEQ_LERP", "MEAN"]
