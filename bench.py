@@ -435,10 +435,10 @@ def run_ours(args):
         if world > 1:
             cache.all_reduce(group)
         regmean = bench_regmean(vlm, model, cfg, cache, dev, group, world, args)
-        if world == 1 and args.model == "base":
-            regmean.update(bench_regmean_chain(vlm, model, cfg, cache, dev, step, dev_batches, B))
         if world == 1 and not args.no_gramfile:
             gram_file = bench_gramfile(vlm, cache, dev)
+        if world == 1 and args.model == "base":
+            regmean.update(bench_regmean_chain(vlm, model, cfg, cache, dev, step, dev_batches, B))
         cache.reset()
 
     # ---- Gram caching on the fused vision-language route (type_id 2) ----

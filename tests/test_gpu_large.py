@@ -34,7 +34,7 @@ def _blocks(d):
 
 
 def test_vitl_interpolation_bit_exact_vs_oracle(large_sd):
-    """All 51 experts -> 24 x 15 merged tensors, 3-source layers (21-23) with the 2/3 a, 2/3 (1-a), 1/3 ratios."""
+    """All 51 experts -> 24 x 13 merged tensors, 3-source layers (21-23) with the 2/3 a, 2/3 (1-a), 1/3 ratios."""
     cfg, sd = large_sd
     np_sd = {k: v.cpu().numpy() for k, v in sd.items()}
     want = oracle.merge_weights(np_sd, LARGE_CFG, num_layers=24)
@@ -42,14 +42,14 @@ def test_vitl_interpolation_bit_exact_vs_oracle(large_sd):
     got = vlm.merge_weights(sd, LARGE_CFG, num_layers=24, stats=stats)
     assert list(got.keys()) == list(want.keys())
     keys = _blocks(want)
-    assert len(keys) == 24 * 15
+    assert len(keys) == 24 * 13            # 7 key templates -> 13 tensors per layer (vilt_module.py:376-384)
     assert stats["merge_bytes"] == 4 * sum((3 if int(k.split(".")[2]) >= 21 else 2) * want[k].size + want[k].size for k in keys)
     for k in keys:
         assert np.array_equal(got[k].cpu().numpy(), want[k]), k
     used = dict(LARGE_CFG, only_activate_used_experts=True)
     want = oracle.merge_weights(np_sd, used, num_layers=24)
     got = vlm.merge_weights(sd, used, num_layers=24)
-    for k in keys[-45:]:                             # layers 21-23: the branch that differs
+    for k in keys[-39:]:                             # layers 21-23: the branch that differs
         assert np.array_equal(got[k].cpu().numpy(), want[k]), k
 
 
@@ -106,9 +106,9 @@ def test_irtr_5k_x_25k_similarity_and_recalls():
     gen = torch.Generator(device="cuda").manual_seed(11)
     n_img, per = 5000, 5
     base = torch.randn(n_img, 768, device="cuda", generator=gen)
-    img = torch.nn.functional.normalize(base + 0.8 * torch.randn(n_img, 768, device="cuda", generator=gen), dim=-1)
+    img = torch.nn.functional.normalize(base + 2.0 * torch.randn(n_img, 768, device="cuda", generator=gen), dim=-1)
     txt = torch.nn.functional.normalize(base.repeat_interleave(per, 0) +
-                                        1.5 * torch.randn(n_img * per, 768, device="cuda", generator=gen), dim=-1)
+                                        3.0 * torch.randn(n_img * per, 768, device="cuda", generator=gen), dim=-1)
     iids = np.arange(n_img)
     tiids = np.arange(n_img * per) // per
     scores, recalls = vlm.irtr_recall(img, txt, iids, tiids)
@@ -116,5 +116,5 @@ def test_irtr_5k_x_25k_similarity_and_recalls():
     ref_scores, ref_recalls = oracle.irtr_recall(img.cpu().numpy(), txt.cpu().numpy(), iids, tiids)
     assert np.abs(scores.cpu().numpy() - ref_scores).max() < 1e-3
     got = np.array([float(r) for r in recalls])
-    assert 0.05 < got.min() and got.max() < 1.0                      # a non-trivial retrieval problem
+    assert 0.02 < got.min() and got.max() < 0.995                    # a non-trivial retrieval problem
     assert np.allclose(got, np.array(ref_recalls, dtype=np.float64), atol=2.0 / n_img), (got, ref_recalls)

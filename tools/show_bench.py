@@ -20,6 +20,6 @@ for text in texts:
         m = d.get("merge") or {}
         if m:
             print(f"  merge: {m['value']} GB/s frac={m['roofline']['frac']} e2e={m['e2e']}")
-        for k in ("reference_hook_on_gpu", "regmean", "gram_file", "fused_route", "irtr", "forward_variants", "cpu_baseline", "gram_parity_rel_fro", "clocks"):
+        for k in ("reference_hook_on_gpu", "regmean", "gram_file", "fused_route", "irtr", "vitl", "forward_variants", "gram_parity_rel_fro_reduced", "cpu_baseline", "gram_parity_rel_fro", "clocks"):
             if d.get(k):
                 print(f"  {k}: {d[k]}")

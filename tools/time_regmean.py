@@ -24,7 +24,7 @@ sd = {k: v.detach() for k, v in model.state_dict().items()}
 mcfg = dict(vlffn_start_layer_index=cfg["vlffn_start_layer_index"], scaling_for_non_diag=0.9,
             loss_names={"irtr": 1, "vqa": 0, "nlvr2": 0})
 L = cfg["num_layers"]
-for n in (1, 4, 1, 2, 4, 6, 8, 12):
+for n in (1, 8, 8, 12, 12, 16, 16, 24, 24, 8):
     torch.cuda.synchronize()
     t = time.perf_counter()
     vlm.regmean(sd, mcfg, num_layers=L, gram_matrices=cache, solve_streams=n)
