@@ -80,19 +80,14 @@ extern "C" int vlm_syrk_accum(const void* x, int dtype, int64_t rows, int d, int
   if (int rc = check_syrk_args("vlm_syrk_accum", x, dtype, rows, d, ldx, g, ldg)) return rc;
   if (rows == 0) return 0;
   if (int rc = require_sm100()) return rc;
-  // VLM_SYRK_VARIANT=1 forces the first-generation (single-CTA) kernel; default is a CTA-pair kernel
-  // whenever the activation has whole 128-byte column groups
-  static const int variant = [] {
-    const char* e = getenv("VLM_SYRK_VARIANT");
-    return e ? atoi(e) : 3;
-  }();
+  // the CTA-pair kernel whenever the activation has whole 128-byte column groups, else the single-CTA kernel
   if (dtype == VLM_TF32X2) {
-    VLM_REQUIRE(syrk_tc2_supported(dtype, d, ldx), VLM_ERR_UNSUPPORTED,
+    VLM_REQUIRE(syrk_pair_supported(dtype, d, ldx), VLM_ERR_UNSUPPORTED,
                 "vlm_syrk_accum: VLM_TF32X2 needs d %% 32 == 0 (got %d); use vlm_syrk_accum_simt on the fp32 activation", d);
-    return syrk_tc2_launch(x, dtype, rows, d, ldx, 0, 0, g, ldg, static_cast<cudaStream_t>(stream));
+    return syrk_pair_launch(x, dtype, rows, d, ldx, 0, 0, g, ldg, static_cast<cudaStream_t>(stream));
   }
-  if (variant != 1 && syrk_tc2_supported(dtype, d, ldx))
-    return syrk_tc2_launch(x, dtype, rows, d, ldx, 0, 0, g, ldg, static_cast<cudaStream_t>(stream));
+  if (syrk_pair_supported(dtype, d, ldx))
+    return syrk_pair_launch(x, dtype, rows, d, ldx, 0, 0, g, ldg, static_cast<cudaStream_t>(stream));
   return syrk_tc_launch(x, dtype, rows, d, ldx, g, ldg, static_cast<cudaStream_t>(stream));
 }
 
@@ -123,8 +118,8 @@ extern "C" int vlm_syrk_accum_strided(const void* x, int dtype, int64_t rows, in
               "vlm_syrk_accum_strided: VLM_TF32X2 planes are packed by vlm_tf32_split, they have no row segments");
   if (int rc = require_sm100()) return rc;
   const int elem = dtype == VLM_F32 ? 4 : 2;
-  if (tma_addressable(x, elem, ldx, g, ldg) && ((seg_stride * elem) & 15) == 0 && syrk_tc2_supported(dtype, d, ldx))
-    return syrk_tc2_launch(x, dtype, rows, d, ldx, seg_rows, seg_stride, g, ldg, static_cast<cudaStream_t>(stream));
+  if (tma_addressable(x, elem, ldx, g, ldg) && ((seg_stride * elem) & 15) == 0 && syrk_pair_supported(dtype, d, ldx))
+    return syrk_pair_launch(x, dtype, rows, d, ldx, seg_rows, seg_stride, g, ldg, static_cast<cudaStream_t>(stream));
   // shapes the CTA-pair kernel does not take: one launch per segment through the contiguous entry points
   for (int64_t s = 0; s < rows / seg_rows; ++s) {
     const char* xs = static_cast<const char*>(x) + (size_t)s * seg_stride * elem;
@@ -147,13 +142,13 @@ extern "C" int vlm_syrk_accum_batch(const vlm_syrk_problem* probs, int n, int dt
     if (q.rows == 0) continue;
     const int elem = (dtype == VLM_F32 || dtype == VLM_TF32X2) ? 4 : 2;
     const bool segmented = dtype != VLM_TF32X2 && q.seg_rows > 0 && q.seg_rows < q.rows;
-    VLM_REQUIRE(dtype != VLM_TF32X2 || (tma_addressable(q.x, 4, q.ldx, q.g, q.ldg) && syrk_tc2_supported(dtype, q.d, q.ldx)),
+    VLM_REQUIRE(dtype != VLM_TF32X2 || (tma_addressable(q.x, 4, q.ldx, q.g, q.ldg) && syrk_pair_supported(dtype, q.d, q.ldx)),
                 VLM_ERR_UNSUPPORTED, "vlm_syrk_accum_batch: VLM_TF32X2 needs d %% 32 == 0 and 16-byte aligned planes");
     if (segmented) {
       if (int rc = check_segments("vlm_syrk_accum_batch", dtype, q.rows, q.seg_rows, q.seg_stride)) return rc;
     }
     const bool tma_ok = tma_addressable(q.x, elem, q.ldx, q.g, q.ldg) && (!segmented || ((q.seg_stride * elem) & 15) == 0);
-    if (tma_ok && syrk_tc2_supported(dtype, q.d, q.ldx)) {
+    if (tma_ok && syrk_pair_supported(dtype, q.d, q.ldx)) {
       grouped.push_back(q);
     } else if (segmented) {
       if (int rc = vlm_syrk_accum_strided(q.x, dtype, q.rows, q.d, q.ldx, q.seg_rows, q.seg_stride, q.g, q.ldg, stream))
@@ -164,7 +159,7 @@ extern "C" int vlm_syrk_accum_batch(const vlm_syrk_problem* probs, int n, int dt
     }
   }
   if (grouped.empty()) return 0;
-  return syrk_tc2_batch_launch(grouped.data(), (int)grouped.size(), dtype, static_cast<cudaStream_t>(stream));
+  return syrk_pair_batch_launch(grouped.data(), (int)grouped.size(), dtype, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vlm_syrk_accum_simt(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,

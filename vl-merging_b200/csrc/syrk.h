@@ -37,17 +37,17 @@ struct PairSeg {
 };
 void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairSeg>* segs, std::vector<int>* off);
 
-// CTA-pair kernels (syrk_tc2.cu: cta_group::2 by default, the multicast pair kernel with VLM_SYRK_VARIANT=2);
-// need whole 128-byte column groups
-bool syrk_tc2_supported(int dtype, int d, int64_t ldx);
+// CTA-pair kernel (syrk_pair.cu + syrk_2sm.cuh: one tcgen05.mma.cta_group::2 stream per pair); needs whole 128-byte
+// column groups
+bool syrk_pair_supported(int dtype, int d, int64_t ldx);
 // seg_rows > 0: X is rows/seg_rows row segments of seg_rows rows, seg_stride elements apart (0: contiguous rows)
-int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
+int syrk_pair_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
                     float* g, int64_t ldg, cudaStream_t stream);
 // fp32 -> [2][rows][d] {hi, lo} TF32 planes (the VLM_TF32X2 operand of the pair kernel, syrk_2sm.cuh)
 int tf32_split_launch(const float* x, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride, float* out,
                       cudaStream_t stream);
-// several independent problems (same dtype) in one grid; every problem must satisfy syrk_tc2_supported
-int syrk_tc2_batch_launch(const vlm_syrk_problem* probs, int n, int dtype, cudaStream_t stream);
+// several independent problems (same dtype) in one grid; every problem must satisfy syrk_pair_supported
+int syrk_pair_batch_launch(const vlm_syrk_problem* probs, int n, int dtype, cudaStream_t stream);
 void build_syrk_pair_schedule_host(int64_t kc, int d, int nsm, std::vector<int32_t>* flat, std::vector<int>* off);
 int syrk_simt_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, float* g, int64_t ldg,
                      cudaStream_t stream);

@@ -1,7 +1,7 @@
 // syrk_2sm.cuh — kernel (a), third generation: ONE tcgen05.mma.cta_group::2 instruction stream per CTA pair.
-// Included by syrk_tc2.cu (which owns the host side: tensor maps, schedules, launches) after its PTX wrappers.
+// Included by syrk_pair.cu (which owns the host side: tensor maps, schedules, launches) after its PTX wrappers.
 //
-// The pair kernel of syrk_tc2.cu is paced by what an SM can take in per chunk (48 KB: its own A block, its own B
+// The pair kernel of syrk_pair.cu is paced by what an SM can take in per chunk (48 KB: its own A block, its own B
 // block and the peer's multicast B block; 712 cycles against 548 cycles of tensor work).  Here the
 // two CTAs of a cluster execute one M = 256, N = 256 instruction together: CTA r holds row block 2a+r (its 128
 // rows of A and of D) and column block 2b+r (its half of B); the tensor cores of the pair read the other half of
@@ -117,7 +117,9 @@ __device__ __forceinline__ void umma2(uint32_t d_tmem, uint64_t adesc, uint64_t 
   }
 }
 
-// BATCH as in syrk_tc2_kernel.  SPLIT: tm_x is the 4-D {hi, lo} map (see header); cps is ignored.
+// BATCH = false: one problem, tensor maps in kernel parameters.  BATCH = true: the segments of several problems
+// (e.g. all Grams of the text tower of one forward) share the grid; tensor maps live in global memory (`maps`:
+// [2*pid] = X, [2*pid+1] = G), written by the host before the launch.  SPLIT: tm_x is the 4-D {hi, lo} map (see header); cps is ignored.
 template <int ELEM_BYTES, int FMT, bool BATCH, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 syrk_2sm_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_g1,

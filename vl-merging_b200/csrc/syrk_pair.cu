@@ -1,25 +1,15 @@
-// syrk_tc2.cu — kernel (a), second generation: CTA pairs with TMA multicast.
+// syrk_pair.cu — host side of kernel (a), the CTA-pair SYRK (device code: syrk_2sm.cuh): tensor maps, the
+// K-aligned work decomposition, schedule cache, single and batched launches, and the fp32 -> {hi, lo} split.
 //
-// Same arithmetic and epilogue as syrk_tc.cu (tcgen05.mma kind::tf32 / kind::f16 on MN-major TMA tiles,
-// fp32 accumulators in TMEM, TMA reduce-add into G).  What changes is how bytes reach shared memory,
-// because the first-generation kernel was bound by L2->SM traffic (48 KB per 512 tensor-pipe cycles per
-// SM, issued as 12 small TMA boxes per stage):
-//
-//  * work unit = a 256x256 SUPER-TILE (a, b), b >= a, computed by a cluster of two CTAs: CTA r owns the
-//    row block 2a+r and both column blocks 2b, 2b+1.  The two CTAs need the same B columns, so each
-//    loads ONE B block and multicasts it into both CTAs' shared memory (.multicast::cluster), plus its
-//    own A block: 32 KB from L2 per CTA per stage instead of 48 KB.  On a diagonal super-tile the A
-//    block of CTA r IS B block r: 16 KB per CTA per stage, and CTA 1 only computes its diagonal block
-//    (N = 128) — the block below the diagonal is never formed.
-//  * X is described to TMA as a 3-D tensor {columns-in-group, rows, column groups} (strides 4 B,
-//    pitch, 128 B), so ONE cp.async.bulk.tensor box {128 B, BK rows, groups-per-block} fetches a whole
-//    128-column block in exactly the [group][row][128 B] order the UMMA descriptor wants: 2 TMA
-//    instructions per stage instead of 12.
-//
-// Synchronisation (per CTA): full[s] gets 1 arrival + the bytes of its own A/B loads AND of the peer's
-// multicast half; empty[s] needs 2 arrivals — this CTA's and the peer's tcgen05.commit (multicast
-// commit) — because a slot is overwritten by the peer's multicast as well.  The two CTAs of a cluster
-// walk the same segment list, so they stay in lock-step by construction.
+// Work unit = a 256 x 256 SUPER-TILE (a, b), b >= a, of the block-upper triangle of G, computed by a cluster of two
+// CTAs with ONE tcgen05.mma.cta_group::2 instruction stream (M = 256 over the pair): CTA r holds row block 2a+r
+// (its 128 rows of A and of the accumulator) and column block 2b+r (its half of B).  X is described to TMA as a 3-D
+// tensor {column in group, row, column group} (strides: element, row pitch, 128 B), so ONE cp.async.bulk.tensor box
+// {128 B, BK rows, groups per block} fetches a whole 128-column block in exactly the [group][row][128 B] order of
+// the canonical MN-major UMMA layout: 2 TMA instructions and 32 KB per CTA per stage.  History: a
+// single-CTA kernel (syrk_tc.cu, still the path for widths that are not whole 128-byte column groups), then CTA
+// pairs with two cta_group::1 streams and TMA multicast (48 KB taken in per SM per stage: ingest-bound at 84 % tensor
+// pipe), then this one (93 %).
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -38,13 +28,10 @@ namespace vlm {
 
 namespace {
 
-constexpr int kStages = 4;
-constexpr int kStageBytes = 3 * kBlockBytes;  // [B0][B1][A]
 constexpr int kStagingBytes = 16384;
 constexpr int kThreads = 256;
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 256;
-constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStagingBytes + 256 + 1024;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -68,57 +55,12 @@ __device__ __forceinline__ uint64_t l2_policy(int kind) {  // 0 evict_normal, 1 
     asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
-// one box of a 3-D tensor map; lands in this CTA only
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint64_t* bar, void* smem_dst, int c0, int c1,
-                                            int c2, uint64_t pol) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
-      "l"(pol)
-      : "memory");
-}
-// same, delivered to the same smem offset (and signalling the same mbarrier offset) in every CTA of `mask`
-__device__ __forceinline__ void tma_load_3d_mcast(const CUtensorMap* tm, uint64_t* bar, void* smem_dst, int c0,
-                                                  int c1, int c2, uint16_t mask, uint64_t pol) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
-      " [%0], [%1, {%4, %5, %6}], [%2], %3, %7;" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
-      : "memory");
-}
-// 4-D variants for row-SEGMENTED activations {column in group, row in segment, column group, segment}
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint64_t* bar, void* smem_dst, int c0, int c1,
-                                            int c2, int c3, uint64_t pol) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
-      "r"(c3), "l"(pol)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d_mcast(const CUtensorMap* tm, uint64_t* bar, void* smem_dst, int c0,
-                                                  int c1, int c2, int c3, uint16_t mask, uint64_t pol) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
-      " [%0], [%1, {%4, %5, %6, %7}], [%2], %3, %8;" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
-      "l"(pol)
-      : "memory");
-}
 __device__ __forceinline__ void tma_reduce_add_2d_hint(const CUtensorMap* tm, const void* smem_src, int c0, int c1,
                                                        uint64_t pol) {
   asm volatile(
       "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
       ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(pol)
       : "memory");
-}
-// tcgen05.commit arriving on the mbarrier at this smem offset in every CTA of `mask`
-__device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(mask)
-               : "memory");
 }
 
 // One unit of work of a cluster in a BATCHED launch (several independent Gram problems in one grid): as PairSeg,
@@ -129,246 +71,6 @@ struct BatchSeg {
 };
 __device__ __forceinline__ void tensormap_acquire(const CUtensorMap* tm) {
   asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
-}
-
-// BATCH = false: one problem, tensor maps in kernel parameters.  BATCH = true: the segments of several problems
-// (e.g. all Grams of the text tower of one forward) share the grid; tensor maps live in global memory (`maps`:
-// [2*pid] = X, [2*pid+1] = G), written by the host before the launch.
-template <int ELEM_BYTES, int FMT, bool BATCH>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-syrk_tc2_kernel(const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_g1,
-                const CUtensorMap* __restrict__ maps, const void* __restrict__ segs_raw,
-                const int* __restrict__ seg_off, int d1, int cps1, int l2_hints) {
-  using G = Geo<ELEM_BYTES>;
-  using Seg = typename std::conditional<BATCH, BatchSeg, PairSeg>::type;
-  const Seg* __restrict__ segs = static_cast<const Seg*>(segs_raw);
-  auto map_x = [&](const Seg& sg) -> const CUtensorMap* {
-    if constexpr (BATCH) return maps + 2 * sg.pid; else return &tm_x1;
-  };
-  auto map_g = [&](const Seg& sg) -> const CUtensorMap* {
-    if constexpr (BATCH) return maps + 2 * sg.pid + 1; else return &tm_g1;
-  };
-  auto cols_of = [&](const Seg& sg) -> int {
-    if constexpr (BATCH) return sg.d; else return d1;
-  };
-  auto cps_of = [&](const Seg& sg) -> int {
-    if constexpr (BATCH) return sg.cps; else return cps1;
-  };
-  constexpr int kRows = G::BK;            // rows of X per pipeline stage
-  constexpr int kBlk = kBlockBytes;       // bytes of one 128-column block per stage
-  constexpr int kBox = G::BOX_BYTES;      // bytes of one column group per stage (= LBO of the UMMA descriptor)
-  constexpr int kNumMma = G::NUM_MMA;
-  constexpr int kNStages = kStages;
-  constexpr int kStageB = kStageBytes;    // [B0][B1][A]
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stage_base = smem;
-  uint8_t* staging = smem + kNStages * kStageB;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kNStages;
-  uint64_t* tfull = bars + 2 * kNStages;
-  uint64_t* tempty = bars + 2 * kNStages + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNStages + 4);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();  // 0 / 1: which row block of the super-tile
-  const int cluster_id = blockIdx.x >> 1;
-  const int seg_begin = seg_off[cluster_id];
-  const int seg_end = seg_off[cluster_id + 1];
-
-  if (!BATCH && warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_x1);
-    tma_prefetch_desc(&tm_g1);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kNStages; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 2);  // this CTA's MMA commit + the peer's
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  cluster_sync_all();  // barrier inits visible cluster-wide before any multicast lands
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0 && lane == 0) {
-    // ===== TMA producer =====
-    int stage = 0;
-    uint32_t phase = 0;
-    int cur_pid = -1;
-    const uint64_t pol_x = l2_policy(l2_hints & 3);
-    for (int s = seg_begin; s < seg_end; ++s) {
-      const Seg seg = segs[s];
-      const CUtensorMap* tm_x = map_x(seg);
-      if constexpr (BATCH) {
-        if (seg.pid != cur_pid) {
-          tensormap_acquire(tm_x);
-          cur_pid = seg.pid;
-        }
-      }
-      const bool diag = seg.sa == seg.sb;
-      const int a_group = (2 * seg.sa + (int)rank) * G::GB;       // first column group of this CTA's A block
-      const int b_group = (2 * seg.sb + (int)rank) * G::GB;       // ... of the B block this CTA fetches
-      const uint32_t bytes = (diag ? 2u : 3u) * kBlk;             // both B blocks (+ own A block)
-      // segmented activation: chunk k = (row segment k / cps, chunk k % cps inside it); rows past the end of a
-      // segment are zero-filled by TMA (they lie outside the tensor map's row dimension)
-      const int cps = cps_of(seg);
-      int xseg = cps > 0 ? seg.k0 / cps : 0;
-      int kin = seg.k0 - xseg * cps;
-      for (int k = seg.k0; k < seg.k1; ++k) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full[stage], bytes);
-        uint8_t* sb = stage_base + stage * kStageB;
-        const int row = kin * kRows;
-        if (cps > 0) {
-          tma_load_4d_mcast(tm_x, &full[stage], sb + rank * kBlk, 0, row, b_group, xseg, (uint16_t)0x3, pol_x);
-          if (!diag) tma_load_4d(tm_x, &full[stage], sb + 2 * kBlk, 0, row, a_group, xseg, pol_x);
-        } else {
-          tma_load_3d_mcast(tm_x, &full[stage], sb + rank * kBlk, 0, row, b_group, (uint16_t)0x3, pol_x);
-          if (!diag) tma_load_3d(tm_x, &full[stage], sb + 2 * kBlk, 0, row, a_group, pol_x);
-        }
-        if (++kin == cps) {
-          kin = 0;
-          ++xseg;
-        }
-        if (++stage == kNStages) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    // The WHOLE warp walks the loop and one elected lane issues: with warp-uniform control flow the descriptors
-    // live in uniform registers.  (Issued from inside an `if (lane == 0)` region every tcgen05.mma cost ~23 SASS
-    // instructions of ELECT / R2UR.BROADCAST / descriptor arithmetic, and the issue loop took about as long as
-    // the MMAs themselves: ncu showed the issuing warp busy, not waiting, while the tensor pipe idled 16 %.)
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    const uint32_t stage0 = smem_u32(stage_base);
-    // descriptor words that never change: high word = SBO | version | layout type, low word = LBO (start address added)
-    constexpr uint32_t kDescHi = (uint32_t)((G::SBO_BYTES >> 4) & 0x3FFF) | (1u << 14) | ((uint32_t)G::LAYOUT_TYPE << 29);
-    constexpr uint32_t kDescLo = (uint32_t)((kBox >> 4) & 0x3FFF) << 16;
-    for (int s = seg_begin; s < seg_end; ++s) {
-      const Seg seg = segs[s];
-      const int sa_t = __shfl_sync(0xffffffffu, seg.sa, 0), sb_t = __shfl_sync(0xffffffffu, seg.sb, 0);
-      const int k0 = __shfl_sync(0xffffffffu, seg.k0, 0), k1 = __shfl_sync(0xffffffffu, seg.k1, 0);
-      const bool diag = sa_t == sb_t;
-      // diagonal super-tile: CTA 1 forms only its diagonal block (B block 1, N = 128)
-      const int n_off = (diag && rank == 1) ? 1 : 0;
-      const uint32_t idesc = make_idesc(FMT, 128 * (2 - n_off));
-      const uint32_t d_tmem = tmem_base + acc * kAccCols;
-      const uint32_t a_off = diag ? rank * kBlk : 2 * kBlk;
-      const uint32_t b_off = n_off * kBlk;
-      mbar_wait(&tempty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      for (int k = k0; k < k1; ++k) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        const uint32_t sb = stage0 + stage * kStageB;
-        const uint32_t alo = (((sb + a_off) & 0x3FFFFu) >> 4) | kDescLo;
-        const uint32_t blo = (((sb + b_off) & 0x3FFFFu) >> 4) | kDescLo;
-        if (elect_one()) {
-#pragma unroll
-          for (int kk = 0; kk < kNumMma; ++kk) {
-            const uint64_t adesc = ((uint64_t)kDescHi << 32) | (alo + kk * (G::KSTEP_BYTES >> 4));
-            const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (blo + kk * (G::KSTEP_BYTES >> 4));
-            umma<FMT>(d_tmem, adesc, bdesc, idesc, (k > k0 || kk > 0) ? 1u : 0u);
-          }
-          tc_commit_mcast(&empty[stage], (uint16_t)0x3);  // slot free in BOTH CTAs once these MMAs have read it
-        }
-        __syncwarp();
-        if (++stage == kNStages) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-      if (elect_one()) tc_commit(&tfull[acc]);
-      __syncwarp();
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-  } else if (warp >= 4) {
-    // ===== epilogue =====
-    const int q = warp - 4;
-    const int epi_tid = threadIdx.x - 128;
-    const int row = q * 32 + lane;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    uint32_t slab_counter = 0;
-    int cur_pid = -1;
-    const uint64_t pol_g = l2_policy((l2_hints >> 2) & 3);
-    for (int s = seg_begin; s < seg_end; ++s) {
-      const Seg seg = segs[s];
-      const CUtensorMap* tm_g = map_g(seg);
-      const int d = cols_of(seg);
-      if constexpr (BATCH) {
-        if (epi_tid == 0 && seg.pid != cur_pid) {
-          tensormap_acquire(tm_g);
-          cur_pid = seg.pid;
-        }
-      }
-      const bool diag = seg.sa == seg.sb;
-      const int n_off = (diag && rank == 1) ? 1 : 0;
-      const int w = 2 - n_off;
-      const int row0 = (2 * seg.sa + (int)rank) * 128;
-      const int col0 = (2 * seg.sb + n_off) * 128;
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      const int nslab = (row0 < d) ? min(4 * w, (d - col0 + 31) / 32) : 0;
-      // After this CTA's LAST segment the pipeline stages are dead (every load was consumed by the MMAs that
-      // tfull just reported complete, in this CTA and — for the multicast halves — in the peer), so each slab
-      // gets its own 16 KB staging slot there and no slab waits for an earlier TMA store to drain.
-      const bool last = (s == seg_end - 1);
-      for (int sl = 0; sl < nslab; ++sl) {
-        uint8_t* buf = last ? stage_base + sl * kStagingBytes : staging + (slab_counter & 1) * kStagingBytes;
-        if (!last) {
-          if (epi_tid == 0) bulk_wait_group_read<1>();
-          named_bar_sync(1, 128);
-        }
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols + sl * 32, v);
-        tmem_ld_wait();
-        const uint32_t rbase = smem_u32(buf) + row * 128;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint32_t addr = rbase + ((uint32_t)(c ^ (row & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * c]), "r"(v[4 * c + 1]),
-                       "r"(v[4 * c + 2]), "r"(v[4 * c + 3])
-                       : "memory");
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (epi_tid == 0) {
-          tma_reduce_add_2d_hint(tm_g, buf, col0 + sl * 32, row0, pol_g);
-          bulk_commit_group();
-        }
-        ++slab_counter;
-      }
-      tc_fence_before();
-      mbar_arrive(&tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-    if (epi_tid == 0) bulk_wait_group<0>();
-  }
-
-  tc_fence_before();
-  cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's shared memory until here
-  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 }  // namespace
@@ -481,28 +183,10 @@ int l2_hints() {
   return v;
 }
 
-// Which pair kernel: 3 = one cta_group::2 instruction stream per pair (syrk_2sm.cuh, the default), 2 = two
-// cta_group::1 streams with TMA multicast (kept selectable with VLM_SYRK_VARIANT=2 for A/B measurements).
-// VLM_TF32X2 exists only in the 2-SM kernel.
-int pair_variant(int dtype) {
-  static const int v = [] {
-    const char* e = getenv("VLM_SYRK_VARIANT");
-    return (e && atoi(e) == 2) ? 2 : 3;
-  }();
-  return dtype == VLM_TF32X2 ? 3 : v;
-}
-
 typedef void (*PairKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap*, const void*, const int*, int, int,
                            int);
 template <bool BATCH>
-PairKernel pick_kernel(int dtype, int variant, int* smem) {
-  if (variant == 2) {
-    *smem = kSmemBytes;
-    if (dtype == VLM_F32) return syrk_tc2_kernel<4, 2, BATCH>;
-    if (dtype == VLM_BF16) return syrk_tc2_kernel<2, 1, BATCH>;
-    return syrk_tc2_kernel<2, 0, BATCH>;
-  }
-  *smem = k2SmemBytes;
+PairKernel pick_kernel(int dtype) {
   if (dtype == VLM_TF32X2) return syrk_2sm_kernel<4, 2, BATCH, true>;
   if (dtype == VLM_F32) return syrk_2sm_kernel<4, 2, BATCH, false>;
   if (dtype == VLM_BF16) return syrk_2sm_kernel<2, 1, BATCH, false>;
@@ -529,10 +213,8 @@ PairKernel pick_kernel(int dtype, int variant, int* smem) {
 // buffered TMEM accumulator), which bounds the tensor core's truncating fp32 accumulation.
 // Measured against the alternatives on the B200 (36928 x 3072 fp32): panel-major stream-K with chunk-granular
 // shares 672 TFLOP/s (many short segments whose 128 KB epilogues cannot hide), this schedule 753-758; an L2
-// look-ahead prefetch (cp.async.bulk.prefetch.tensor) cost 8 %, half-height stages x 8 cost 14 %.  A variant
-// issuing ONE tcgen05.mma.cta_group::2 (M = 256) per K step for the pair (32 KB stages x 6, no multicast) was
-// bit-for-bit as accurate but ran at exactly half the speed (380 TFLOP/s, tensor pipe 37 % active in ncu) with
-// these MN-major operands, so the pair keeps two independent cta_group::1 instruction streams.
+// look-ahead prefetch (cp.async.bulk.prefetch.tensor) cost 8 %, half-height stages x 8 cost 14 %.  (Numbers of the
+// multicast pair kernel of round 1; the cta_group::2 kernel keeps the schedule unchanged.)
 void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairSeg>* segs, std::vector<int>* off) {
   // chunks per accumulation: 4096 fp32 rows / 8192 16-bit rows.  Measured on the B200 with all-positive
   // activations 36928 x 3072: cap 128 / 256 / 512 / none -> rel. error 7.6e-4 / 7.8e-4 / 8.2e-4 / 1.0e-3 (fp32),
@@ -634,7 +316,7 @@ void build_syrk_pair_schedule_host(int64_t kc, int d, int nsm, std::vector<int32
   }
 }
 
-bool syrk_tc2_supported(int dtype, int d, int64_t ldx) {
+bool syrk_pair_supported(int dtype, int d, int64_t ldx) {
   return d % (128 / elem_bytes(dtype)) == 0 && ldx >= d;  // whole 128-byte column groups (the 3-D tensor map needs them)
 }
 
@@ -649,7 +331,7 @@ static inline void seg_chunks(int64_t rows, int64_t seg_rows, int bk, int64_t* c
   }
 }
 
-int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
+int syrk_pair_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
                     float* g, int64_t ldg, cudaStream_t stream) {
   const int elem = elem_bytes(dtype);
   const int bk = chunk_rows(dtype);
@@ -664,8 +346,8 @@ int syrk_tc2_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, 
   VLM_REQUIRE(kc < (int64_t)1 << 30, VLM_ERR_INVALID_ARG, "vlm_syrk_accum: too many row chunks");
   CUtensorMap tm_x, tm_g;
   if (int rc = encode_maps(x, dtype, rows, d, ldx, seg_rows, seg_stride, g, ldg, &tm_x, &tm_g)) return rc;
-  int smem = 0;
-  PairKernel kernel = pick_kernel<false>(dtype, pair_variant(dtype), &smem);
+  const int smem = k2SmemBytes;
+  PairKernel kernel = pick_kernel<false>(dtype);
 
   // lookup and launch under one lock: an eviction by another host thread cannot free a schedule between the two
   std::lock_guard<std::mutex> lk(g_mu2);
@@ -716,7 +398,7 @@ int tf32_split_launch(const float* x, int64_t rows, int d, int64_t ldx, int64_t 
   return 0;
 }
 
-int syrk_tc2_batch_launch(const vlm_syrk_problem* probs, int n, int dtype, cudaStream_t stream) {
+int syrk_pair_batch_launch(const vlm_syrk_problem* probs, int n, int dtype, cudaStream_t stream) {
   const int elem = elem_bytes(dtype);
   const int bk = chunk_rows(dtype);
   int dev = 0, nsm = 0;
@@ -803,8 +485,8 @@ int syrk_tc2_batch_launch(const vlm_syrk_problem* probs, int n, int dtype, cudaS
   }
   // pageable source: staged before the call returns; ordered on `stream` before the kernel below
   VLM_CUDA(cudaMemcpyAsync(dptr, host.data(), total, cudaMemcpyHostToDevice, stream));
-  int smem = 0;
-  PairKernel kernel = pick_kernel<true>(dtype, pair_variant(dtype), &smem);
+  const int smem = k2SmemBytes;
+  PairKernel kernel = pick_kernel<true>(dtype);
   VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kernel<<<2 * ncl, kThreads, smem, stream>>>(maps[0], maps[1], reinterpret_cast<const CUtensorMap*>(dptr),
                                               dptr + maps_bytes + off_bytes,

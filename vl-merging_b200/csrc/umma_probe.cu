@@ -5,7 +5,7 @@
 //
 // Every CTA pair (cluster of 2, one CTA per SM, all 148 SMs) spins on MMAs over four resident 48 KB stage buffers —
 // no loads, no epilogue — for the operand layouts in question:
-//   group 1 : each CTA issues its own M = 128, N = 256 instructions (what syrk_tc2_kernel does)
+//   group 1 : each CTA issues its own M = 128, N = 256 instructions (the round-1 multicast pair kernel)
 //   group 2 : the leader issues ONE M = 256, N = 256 cta_group::2 instruction for the pair (each CTA holds its 128 A rows
 //             and half of B)
 //   MN-major (the Gram layout: X^T X with X row-major) vs K-major (the usual GEMM layout), tf32 vs bf16,
@@ -159,7 +159,7 @@ probe_kernel(int iters, const uint8_t* __restrict__ src) {
   const uint32_t tmem = *slot;
 
   // descriptors.  MN-major: LBO = one column group of BK rows (BK*128 B), SBO = one swizzle atom of rows; layout
-  // SWIZZLE_128B_BASE32B (1) for tf32, SWIZZLE_128B (2) for 16-bit — exactly syrk_tc2_kernel's.  K-major: 128-byte
+  // SWIZZLE_128B_BASE32B (1) for tf32, SWIZZLE_128B (2) for 16-bit — exactly the SYRK kernels'.  K-major: 128-byte
   // rows (32 tf32 / 64 bf16 K elements), 8-row atoms 1024 B apart, SWIZZLE_128B; one MMA advances K by 32 bytes.
   constexpr uint32_t kLayout = MN ? (TF32 ? 1u : 2u) : 2u;
   constexpr uint32_t kLbo = MN ? (uint32_t)((TF32 ? 32 : 64) * 128) : 16u;
