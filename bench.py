@@ -268,6 +268,19 @@ def run_ours(args):
     cache.timing = False
     launches = vlm._lib.launch_count() - launches0
     n_live, reduce_bytes = len(cache.live_names()), getattr(cache, "last_reduce_bytes", 0)
+    ar_alone_ms = None
+    if world > 1:
+        # the exchange step on its own, ranks aligned by a barrier first (the in-region figure also contains the wait
+        # for the slowest rank's last step); the values are garbage afterwards, the cache is reset before its next use
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        cache.all_reduce(group)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ar_alone_ms = round(t.item(), 3)
     clocks = sampler.stop(t0, t1) if sampler else None
     value = world * B * args.steps / (ms * 1e-3)
 
@@ -499,7 +512,7 @@ def run_ours(args):
                        "gram_hooks": (f"activations <= {args.defer_mb} MB are held by reference and issued as grouped launches "
                                       f"(flush at {args.defer_cap_mb} MB pending and after every forward); larger ones launch "
                                       "from the hook") if args.defer_mb > 0 else "one SYRK launch per hook call",
-                       "allreduce_ms_in_timed_region": round(ar_ms, 3),
+                       "allreduce_ms_in_timed_region": round(ar_ms, 3), "allreduce_ms_after_barrier": ar_alone_ms,
                        "allreduce": (f"packed upper triangles of the {n_live} live Grams in one NCCL all-reduce "
                                      f"({reduce_bytes / 1e6:.0f} MB)") if world > 1 else None},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
@@ -629,22 +642,74 @@ def bench_irtr(vlm, model, cfg, dev, group, world, args, n_img=5000, per_img=5, 
     torch.cuda.synchronize(dev)
     t_merge = time.perf_counter() - t0
     ufo = central
-    # synthetic eval set: 2 distinct image batches and 2 text batches cycled (content does not matter for timing)
+    # synthetic eval set: every item distinct (so that the score matrix has no exact ties), generated on the device
+    # batch by batch from two hash-seeded base batches: image i = base + noise_i, caption ids re-drawn per batch
     ib = [vlm.synthetic_batch(bs, cfg, seed=900 + i, device=dev) for i in range(2)]
     tb = [vlm.synthetic_batch(bs, cfg, seed=950 + i, device=dev, pad=True) for i in range(2)]
     n_ib, n_tb = (n_img + bs - 1) // bs, (n_img * per_img + bs - 1) // bs
-    image_batches = [ib[i % 2] for i in range(n_ib)]
-    text_batches = [tb[i % 2] for i in range(n_tb)]
+
+    class Lazy:
+        def __init__(self, n, make):
+            self.n, self.make = n, make
+
+        def __len__(self):
+            return self.n
+
+        def __iter__(self):
+            return (self.make(i) for i in range(self.n))
+
+    def make_image(i):
+        gen = torch.Generator(device=dev).manual_seed(7000 + i)
+        return {**ib[i % 2], "image": [ib[i % 2]["image"][0] + 0.25 * torch.randn(ib[0]["image"][0].shape, device=dev, generator=gen)]}
+
+    def make_text(i):
+        gen = torch.Generator(device=dev).manual_seed(9000 + i)
+        base = tb[i % 2]
+        ids = torch.randint(999, cfg["vocab_size"] - 1, base["text_ids"].shape, device=dev, generator=gen) * base["text_masks"]
+        ids[:, 0] = 101
+        return {**base, "text_ids": ids}
+
+    image_batches, text_batches = Lazy(n_ib, make_image), Lazy(n_tb, make_text)
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     img, txt = vlm.irtr_features(ufo, image_batches, text_batches, autocast_dtype=torch.float16, group=group)
     img, txt = img[:n_img], txt[: n_img * per_img]
-    scores, recalls = vlm.irtr_recall(img.float(), txt.float(), np.arange(n_img), np.arange(n_img * per_img) // per_img)
     torch.cuda.synchronize(dev)
-    dt = time.perf_counter() - t0
-    return {"merge_seconds": round(t_merge, 4), "eval_seconds": round(dt, 3), "images": n_img, "captions": n_img * per_img,
-            "scores_shape": list(scores.shape), "forwards_per_sec": round((n_img + n_img * per_img) / dt, 1),
-            "autocast": "fp16 (as objectives.py:657,669)", "recalls": [round(float(r), 5) for r in recalls]}
+    t_towers = time.perf_counter() - t0
+    iids, tiids = np.arange(n_img), np.arange(n_img * per_img) // per_img
+
+    def timed_ms(fn, reps=3):
+        fn()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            out = fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / reps, out
+
+    # objectives.py:684-710 two ways on the same features: the reference's form (materialised 5k x 25k scores + six
+    # topk calls, stock torch) and the fused kernel (vlm_sim_topk twice, no score matrix)
+    ms_plain, (scores, recalls) = timed_ms(lambda: vlm.irtr_recall(img.float(), txt.float(), iids, tiids))
+    ms_fused, (recalls_f, (by_image, _)) = timed_ms(lambda: vlm.irtr_recall_fused(img, txt, iids, tiids))
+    # random-init towers give nearly identical features (recalls at chance level, many near-ties), so the check is on
+    # the scores of the chosen columns: every row's ten fused picks must score what the materialised matrix says
+    top_f = torch.gather(scores, 1, by_image)
+    top_t = scores.topk(10, dim=1).values
+    pick_err = float((top_f - top_t).abs().max().item())
+    dt = t_towers + ms_fused * 1e-3
+    flops = 2 * 2.0 * n_img * n_img * per_img * img.shape[1]
+    return {"merge_seconds": round(t_merge, 4), "eval_seconds": round(dt, 3), "towers_seconds": round(t_towers, 3),
+            "images": n_img, "captions": n_img * per_img, "scores_shape": list(scores.shape),
+            "forwards_per_sec": round((n_img + n_img * per_img) / t_towers, 1),
+            "autocast": "fp16 (as objectives.py:657,669)", "recalls": [round(float(r), 5) for r in recalls_f],
+            "similarity_topk": {"fused_ms": round(ms_fused, 3), "torch_scores_plus_6_topk_ms": round(ms_plain, 3),
+                                "fused_tflops": round(flops / (ms_fused * 1e-3) * 1e-12, 1),
+                                "recalls_torch_path": [round(float(r), 5) for r in recalls],
+                                "top10_score_max_abs_diff_vs_torch": pick_err,
+                                "note": "vlm_sim_topk (TMA + tcgen05 kind::f16, running top-10 in the accumulator epilogue), both "
+                                        "directions, vs img @ txt.T (500 MB fp32) + topk x 6 in torch"}}
 
 
 def bench_regmean(vlm, model, cfg, cache, dev, group, world, args):

@@ -195,6 +195,20 @@ int vlm_spd_solve_right(double* s, int in_f, int64_t lds, double* r, int out_f, 
 int vlm_spd_solve_right_async(double* s, int in_f, int64_t lds, double* r, int out_f, int64_t ldr,
                               int* info_dev, void* stream);
 
+/* ---- retrieval step after the merge ------------------------------------
+ * Replaces, in compute_irtr_recall (src/vilt/modules/objectives.py:684-710),
+ *     scores = img_cls_feats @ txt_cls_feats.t();  scores.topk(k, dim=1)  (k = 1, 5, 10)
+ * and, with the operands swapped, scores.topk(k, dim=0): the ten best rows of B for every row of A, by
+ * A[i] . B[j], straight from the tensor-core accumulators — the m x n score matrix (500 MB for 5,000 x 25,000) is
+ * never written.  a [m, d], b [n, d]: VLM_F16 or VLM_BF16 (what the towers produce under the reference's autocast),
+ * row-major, 16-byte aligned, lda / ldb multiples of 8.  Products exact, fp32 accumulation.
+ * out_val / out_idx: [m][splits][10] — per row `splits` partial lists (one per range of B), each sorted descending
+ * with the lower index first among equal scores, padded with -inf / -1; splits = vlm_sim_topk_splits(m, n)
+ * (chosen so that few row blocks still fill the GPU).  The caller merges the partial lists. */
+int vlm_sim_topk_splits(int64_t m, int64_t n);
+int vlm_sim_topk(const void* a, int64_t m, int64_t lda, const void* b, int64_t n, int64_t ldb, int d, int dtype,
+                 float* out_val, int32_t* out_idx, int splits, void* stream);
+
 /* Pivoted-LU variant for a summed Gram that Cholesky rejects (VLM_ERR_NOT_SPD / potrf status > 0): the reference
  * inverts with torch.inverse (LU; src/vilt/modules/vilt_module.py:432,483), which succeeds on any numerically
  * non-singular matrix.  s must hold the FULL symmetric matrix again (potrf overwrote a triangle); both s and r are
