@@ -102,3 +102,41 @@ def test_layout_single_rank_is_identity():
     flat = torch.arange(layout.shard_size[0], dtype=torch.float32)
     assert layout.gather(flat, 0, None) is flat
     assert all(layout.offset[i] % 4 == 0 for i in range(len(SIZES)))  # 16-byte aligned segments
+
+
+def _ragged_job(rank, world):
+    """Buffers created lazily exist only where the module fired: rank 0 holds {a, only0}, rank 1 holds {a, only1}.
+    The reduction first agrees on the union, so both ranks issue the same collectives and end up with the same keys."""
+    buffers = {"a": torch.full((4, 4), float(rank + 1))}
+    calls, rows = {"a": 1}, {"a": 3}
+    buffers[f"only{rank}"] = torch.full((2 + rank, 2 + rank), 10.0 * (rank + 1))
+    calls[f"only{rank}"], rows[f"only{rank}"] = 1, 5
+    from collections import defaultdict
+    calls, rows = defaultdict(int, calls), defaultdict(int, rows)
+    reduce_gram_buffers(buffers, [], calls, rows, None)
+    return {k: v.numpy().copy() for k, v in buffers.items()}, dict(calls), dict(rows)
+
+
+def test_ranks_with_different_buffer_sets_agree_first():
+    res = _spawn(_ragged_job)
+    for rank in range(2):
+        bufs, calls, rows = res[rank]
+        assert sorted(bufs) == ["a", "only0", "only1"]
+        assert np.array_equal(bufs["a"], np.full((4, 4), 3.0, np.float32))
+        assert np.array_equal(bufs["only0"], np.full((2, 2), 10.0, np.float32))
+        assert np.array_equal(bufs["only1"], np.full((3, 3), 20.0, np.float32))
+        assert calls == {"a": 2, "only0": 1, "only1": 1} and rows == {"a": 6, "only0": 5, "only1": 5}
+
+
+def _mismatch_job(rank, world):
+    buffers = {"a": torch.zeros(4 + rank, 4 + rank)}
+    try:
+        reduce_gram_buffers(buffers, [], {"a": 0}, {"a": 0}, None)
+    except RuntimeError as e:
+        return str(e)
+    return None
+
+
+def test_width_mismatch_between_ranks_raises_instead_of_hanging():
+    res = _spawn(_mismatch_job)
+    assert all("width" in (res[r] or "") for r in range(2)), res

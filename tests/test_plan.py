@@ -100,3 +100,35 @@ def test_vit_large_layer_count():
 def test_package_imports_without_cuda():
     assert vlm.__version__
     assert callable(vlm.merge_weights) and callable(vlm.GramCache)
+
+
+def test_independent_unshares_views_of_one_host_buffer():
+    import torch
+
+    from vl_merging_b200.merge import independent
+
+    flat = torch.arange(12, dtype=torch.float32)
+    sd = {"a": flat[:4].view(2, 2), "b": flat[4:].view(2, 4), "own": torch.ones(3), "n": 5}
+    out = independent(sd)
+    assert list(out) == list(sd) and out["n"] == 5 and out["own"] is sd["own"]
+    for k in ("a", "b"):
+        assert torch.equal(out[k], sd[k]) and out[k].untyped_storage().data_ptr() != flat.untyped_storage().data_ptr()
+        assert out[k].untyped_storage().nbytes() == out[k].numel() * 4
+
+
+def test_device_resolution_follows_local_rank(monkeypatch):
+    import torch
+
+    from vl_merging_b200 import merge
+
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "device_count", lambda: 8)
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    cpu_sd = {"w": torch.zeros(2)}
+    monkeypatch.setenv("LOCAL_RANK", "5")
+    assert merge._resolve_device(cpu_sd, None) == torch.device("cuda", 5)      # not everybody on cuda:0
+    monkeypatch.setenv("LOCAL_RANK", "11")                                      # out of range: ignore
+    assert merge._resolve_device(cpu_sd, None) == torch.device("cuda", 0)
+    monkeypatch.delenv("LOCAL_RANK")
+    assert merge._resolve_device(cpu_sd, None) == torch.device("cuda", 0)
+    assert merge._resolve_device(cpu_sd, "cuda:3") == torch.device("cuda", 3)   # an explicit device always wins
