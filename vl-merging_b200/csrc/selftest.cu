@@ -362,6 +362,66 @@ static void syrk_f64_case(const char* name, int dtype, int nseg, int n_tok, int 
   CK(cudaFree(g));
 }
 
+
+// Grouped launch of n1 problems (rows1 x d1) + n2 problems (rows2 x d2), all fp32, distinct activations and Grams:
+// correctness of every Gram against the single-launch kernel, and the rate of the group (what GramCache's deferred
+// flush issues: e.g. 9 x [36928, 768] for a slice of the image tower, 36 x [2560, 768] + 12 x [2560, 3072] for the text tower).
+static void syrk_batch_case(int n1, int64_t rows1, int d1, int n2, int64_t rows2, int d2, int iters) {
+  const int n = n1 + n2;
+  std::vector<vlm_syrk_problem> pr(n);
+  std::vector<float*> xs(n), gs(n), refs(n);
+  double flops = 0;
+  for (int p = 0; p < n; ++p) {
+    const int64_t rows = p < n1 ? rows1 : rows2;
+    const int d = p < n1 ? d1 : d2;
+    std::vector<float> hx((size_t)rows * d);
+    fill_x<float>(hx, p & 1);
+    CK(cudaMalloc(&xs[p], hx.size() * 4));
+    CK(cudaMemcpy(xs[p], hx.data(), hx.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&gs[p], (size_t)d * d * 4));
+    CK(cudaMalloc(&refs[p], (size_t)d * d * 4));
+    CK(cudaMemset(gs[p], 0, (size_t)d * d * 4));
+    CK(cudaMemset(refs[p], 0, (size_t)d * d * 4));
+    pr[p] = vlm_syrk_problem{xs[p], rows, d, gs[p], d, d, 0, 0, 0};
+    flops += (double)rows * d * (d + 1.0);
+    VK(vlm_syrk_accum(xs[p], VLM_F32, rows, d, d, refs[p], d, nullptr));
+  }
+  VK(vlm_syrk_accum_batch(pr.data(), n, VLM_F32, nullptr));
+  CK(cudaDeviceSynchronize());
+  double worst = 0;
+  for (int p = 0; p < n; ++p) {
+    const int d = p < n1 ? d1 : d2;
+    std::vector<float> a((size_t)d * d), b((size_t)d * d);
+    CK(cudaMemcpy(a.data(), gs[p], a.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(b.data(), refs[p], b.size() * 4, cudaMemcpyDeviceToHost));
+    double num = 0, den = 0;
+    for (int r = 0; r < d; ++r)
+      for (int c = r; c < d; ++c) {
+        const double e = (double)a[(size_t)r * d + c] - b[(size_t)r * d + c];
+        num += e * e;
+        den += (double)b[(size_t)r * d + c] * b[(size_t)r * d + c];
+      }
+    worst = std::max(worst, sqrt(num / den));
+  }
+  float ms = 0;
+  if (iters > 0) {
+    Timer t;
+    for (int i = 0; i < 2; ++i) VK(vlm_syrk_accum_batch(pr.data(), n, VLM_F32, nullptr));
+    t.start();
+    for (int i = 0; i < iters; ++i) VK(vlm_syrk_accum_batch(pr.data(), n, VLM_F32, nullptr));
+    ms = t.stop() / iters;
+  }
+  const bool ok = worst < 5e-5;   // same kernel, same operands: only segment boundaries and the order of the reduce-adds differ
+  printf("BATCH %d x [%lld, %d] + %d x [%lld, %d]  vs single launches relF=%.2e  %.3f ms  %.1f TFLOP/s(sym)  %s\n", n1,
+         (long long)rows1, d1, n2, (long long)rows2, d2, worst, ms, ms > 0 ? flops / ms * 1e-9 : 0.0, ok ? "OK" : "FAIL");
+  if (!ok) ++g_fail;
+  for (int p = 0; p < n; ++p) {
+    CK(cudaFree(xs[p]));
+    CK(cudaFree(gs[p]));
+    CK(cudaFree(refs[p]));
+  }
+}
+
 // Row-sliced activation: the view h[:, off:off+seg_rows] of an (nseg, n_tok, d) tensor, read in place
 // (vlm_syrk_accum_strided, and the same problem through vlm_syrk_accum_batch) against a host fp64 Gram of the
 // slice (host_ref) or the contiguous kernel on a packed copy of the slice.
@@ -697,6 +757,10 @@ int main(int argc, char** argv) {
     else syrk_case<__half>("case f16", VLM_F16, rows, d, mode, false, iters, 1e-4);
     return g_fail;
   }
+  if (argc >= 9 && !strcmp(argv[1], "batch")) {  // selftest batch <n1> <rows1> <d1> <n2> <rows2> <d2> <iters>
+    syrk_batch_case(atoi(argv[2]), atoll(argv[3]), atoi(argv[4]), atoi(argv[5]), atoll(argv[6]), atoi(argv[7]), atoi(argv[8]));
+    return g_fail;
+  }
   if (argc >= 6 && !strcmp(argv[1], "f64")) {  // selftest f64 <f32|bf16> <rows> <d> <iters> [positive]
     const int rows = atoi(argv[3]), d = atoi(argv[4]), iters = atoi(argv[5]), mode = argc > 6 ? atoi(argv[6]) : 0;
     if (!strcmp(argv[2], "f32")) syrk_f64_case<float>("case f32", VLM_F32, 1, rows, 0, rows, d, mode, false, iters, 1e-13);
@@ -778,6 +842,9 @@ int main(int argc, char** argv) {
   syrk_strided_case<float>("f32 d=200 (gen-1 path)", VLM_F32, 3, 50, 7, 33, 200, true, 0, 2e-3);
   syrk_strided_case<float>("f32 image slice x64", VLM_F32, 64, 617, 40, 577, 768, false, 20, 2e-4);
   syrk_strided_case<float>("f32 text slice x64", VLM_F32, 64, 617, 0, 40, 768, false, 20, 2e-4);
+
+  // grouped launches: a small mixed group for correctness
+  syrk_batch_case(3, 1000, 768, 2, 333, 256, 0);
 
   // hot shapes: SIMT kernel as the reference, timed
   syrk_case<float>("f32 text d=768", VLM_F32, 2560, 768, 0, false, 20, 2e-3);
