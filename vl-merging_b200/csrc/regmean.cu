@@ -110,10 +110,10 @@ regmean_rhs_kernel(const float* __restrict__ w, int M, int K, int64_t ldw, const
     }
 }
 
-// Pipelined variant for the real layer shapes (K a multiple of 16, 16-byte aligned rows): 128x128 block tile,
+// Pipelined variant for the real layer shapes (K a multiple of 32, 16-byte aligned rows): 128x128 block tile,
 // 16 warps of 32x32, raw fp32 / fp64 tiles brought in by a 3-stage cp.async pipeline; widening to fp64 and
 // scale_G happen when a fragment is read from shared memory, so no converted copy is ever stored.
-constexpr int TM = 128, TN = 128, TK = 16, TSTAGES = 3;
+constexpr int TM = 128, TN = 128, TK = 32, TSTAGES = 3;
 constexpr int W_PITCH = TK + 4;  // floats: fragment reads hit 32 distinct banks
 
 template <typename GT>
@@ -145,13 +145,13 @@ regmean_rhs_pipelined_kernel(const float* __restrict__ w, int M, int K, int64_t 
 
   auto load_stage = [&](int slot, int kt) {
     const int k0 = kt * TK;
-    {  // W tile: 128 rows x 16 floats = 512 chunks, one per thread
-      const int r = tid >> 2, ch = tid & 3;
+    for (int e = tid; e < TM * (TK / 4); e += 512) {  // W tile: 128 rows x 32 floats = 1024 16-byte chunks
+      const int r = e / (TK / 4), ch = e % (TK / 4);
       const bool ok = (m0 + r) < M && k0 < K;
       cp_async16(&sm.w[slot][r][ch * 4], w + (int64_t)(ok ? m0 + r : 0) * ldw + (ok ? k0 : 0) + ch * 4, ok);
     }
     constexpr int chunks_per_row = TN / GV;
-    for (int e = tid; e < TK * chunks_per_row; e += 512) {  // G tile: 16 rows x 128 columns
+    for (int e = tid; e < TK * chunks_per_row; e += 512) {  // G tile: 32 rows x 128 columns
       const int kk = e / chunks_per_row, ch = e % chunks_per_row;
       const bool ok = k0 < K && (n0 + ch * GV) < N;
       cp_async16(&sm.g[slot][kk][ch * GV], g + (int64_t)(ok ? k0 + kk : 0) * ldg + (ok ? n0 + ch * GV : 0), ok);
