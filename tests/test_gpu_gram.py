@@ -151,6 +151,53 @@ def test_deferred_hooks_flush_after_each_forward():
     assert worst < 1e-6, worst
 
 
+def test_deferred_activation_modified_in_place_is_refused():
+    """Deferral keeps a reference, not a copy: an in-place write before the flush would change the Gram silently.
+    The version counter of the held tensor gives it away and flush() raises instead."""
+    cache = vlm.GramCache(defer_bytes=1 << 30)
+    x = torch.randn(4, 64, 128, device="cuda")
+    cache.accumulate("a", x)
+    cache.accumulate("b", torch.randn(256, 128, device="cuda"))
+    x.mul_(2.0)                                   # e.g. an in-place residual / dropout after the hooked module
+    with pytest.raises(RuntimeError, match="modified in place"):
+        cache.flush()
+    assert not cache._pending                     # nothing half-issued is left behind
+    y = torch.randn(256, 128, device="cuda")
+    cache.reset()
+    cache.accumulate("a", y)                      # untouched activations still go through
+    cache.flush()
+    ref = y.double().T @ y.double()
+    assert ((cache.gram("a").double() - ref).norm() / ref.norm()).item() < 1e-3
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "fp64"])
+def test_precision_modes_match_the_fp64_hook(precision):
+    """The RegMean-grade Gram modes on the shapes of the hook path: 3-D inputs, a row slice of a (B, N, D) activation,
+    bf16 inputs, an odd width (tf32x3: CUDA-core fallback; fp64: scalar-load path), immediate and grouped."""
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    joint = torch.randn(6, 617, 256, device="cuda", generator=gen)
+    xs = {"plain": torch.randn(3, 577, 256, device="cuda", generator=gen), "slice": joint[:, 40:],
+          "text": joint[:, :40], "bf16": torch.randn(1000, 128, device="cuda", generator=gen).bfloat16(),
+          "odd": torch.randn(333, 200, device="cuda", generator=gen)}
+    tol = 2e-13 if precision == "fp64" else 5e-6
+    for defer in (0, 1 << 30):
+        if precision == "fp64" and defer:
+            continue
+        cache = vlm.GramCache(precision=precision, defer_bytes=defer)
+        for name, x in xs.items():
+            cache.accumulate(name, x)
+            cache.accumulate(name, x)
+        cache.flush()
+        for name, x in xs.items():
+            x64 = x.double().reshape(-1, x.shape[-1])
+            ref = 2 * (x64.T @ x64)
+            g = cache.gram(name)
+            assert g.dtype == (torch.float64 if precision == "fp64" else torch.float32)
+            err = ((g.double() - ref).norm() / ref.norm()).item()
+            assert err < (tol if name != "bf16" or precision == "fp64" else 1e-5), (precision, defer, name, err)
+            assert torch.equal(g, g.T)
+
+
 @pytest.mark.parametrize("defer", [0, 1 << 40])
 def test_side_stream_mode_matches_in_stream_launches(defer):
     """GramCache(side_stream=True): launches on a second stream, joined by flush() after every forward; the

@@ -132,9 +132,10 @@ class GramCache:
         flush() issues everything pending as one grouped launch (vlm_syrk_accum_batch), in which one problem's
         epilogue overlaps the next one's mainloop.  register() then also flushes after every forward of the
         registered model.
-        Only safe when nothing modifies a hooked activation in place after the hooked module ran — true for the
-        VLMo blocks (LayerNorm / attention / GELU outputs are fresh tensors); the default 0 keeps the
-        reference's immediate semantics.  Deferred activations stay allocated until the flush; a flush is forced
+        Only valid when nothing modifies a hooked activation in place after the hooked module ran — true for the
+        VLMo blocks (LayerNorm / attention / GELU outputs are fresh tensors); flush() checks the version counter of
+        every held activation and raises if one was written to.  The default 0 keeps the reference's immediate
+        semantics.  Deferred activations stay allocated until the flush; a flush is forced
         after max_pending activations or max_pending_bytes of them.
         side_stream=True: the SYRK launches go to a second CUDA stream (ordered after the producer of each
         activation by an event), so they overlap the rest of the forward — its LayerNorm / GELU / softmax
@@ -223,7 +224,7 @@ class GramCache:
                                                     g.data_ptr(), g.stride(0), self._launch_stream(keep)))
             return
         if 0 < nbytes <= self.defer_bytes and not simt:
-            self._pending.append((code, keep, g, ptr, rows, d, ldx, seg_rows, seg_stride))
+            self._pending.append((code, keep, g, ptr, rows, d, ldx, seg_rows, seg_stride, name, keep._version))
             self._pending_bytes += nbytes
             if len(self._pending) >= self.max_pending or self._pending_bytes >= self.max_pending_bytes:
                 self.flush()
@@ -284,6 +285,12 @@ class GramCache:
         if not self._pending:
             return self._join()
         pending, self._pending, self._pending_bytes = self._pending, [], 0
+        for p in pending:   # an in-place write to a held activation bumps its version counter: refuse to use it
+            if p[1]._version != p[10]:
+                raise RuntimeError(
+                    f"GramCache: the activation hooked for {p[9]} was modified in place before the deferred Gram launch "
+                    "(its Gram would be taken of the modified values); use defer_bytes=0 for this model")
+        pending = [p[:9] for p in pending]
         stream = self._launch_stream()
         for code in sorted({p[0] for p in pending}):
             group = [p for p in pending if p[0] == code]
