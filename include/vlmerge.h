@@ -169,6 +169,12 @@ int vlm_merge_plan_destroy(vlm_merge_plan* plan);
 /* algorithmic bytes one run moves: sum over segments of (n_src + 1) * n * 4 */
 uint64_t vlm_merge_plan_bytes(const vlm_merge_plan* plan);
 
+/* n copies dst_base + dst_off_bytes[i] <- src[i] (nbytes[i] each; host or device sources, cudaMemcpyDefault) enqueued
+ * on `stream` in one call: stages the ~400 tensors of a host checkpoint into the merge's input arena.  Pinned sources
+ * copy asynchronously; pageable ones are staged by the driver before the call returns. */
+int vlm_copy_batch(void* dst_base, const uint64_t* dst_off_bytes, const void* const* src_host_or_dev,
+                   const uint64_t* nbytes, int n, void* stream);
+
 /* ---- (c) RegMean ---------------------------------------------------------------------------
  * Replaces, in regmean (src/vilt/modules/vilt_module.py:366-531):
  *   scale_G (:388-392)              Ghat = a*G + (1-a)*diag(G)

@@ -75,6 +75,7 @@ SIGNATURES = {
     "vlm_merge_plan_run": (c_int, [c_void_p, c_void_p]),
     "vlm_merge_plan_destroy": (c_int, [c_void_p]),
     "vlm_merge_plan_bytes": (c_uint64, [c_void_p]),
+    "vlm_copy_batch": (c_int, [c_void_p, POINTER(c_uint64), POINTER(c_void_p), POINTER(c_uint64), c_int, c_void_p]),
     "vlm_gram_scale_accum": (c_int, [c_void_p, c_int, c_int, c_int64, c_double, c_void_p, c_int64, c_int, c_void_p]),
     "vlm_regmean_rhs": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_int, c_int64, c_double, c_void_p,
                                 c_int64, c_int, c_void_p]),

@@ -109,6 +109,14 @@ def _run_elementwise(ops, lookup, shapes, device, out_device, group=None, stats=
     import torch.distributed as dist
 
     lib = _lib.lib()
+    trace = stats.get("trace") if stats is not None else None     # optional: host timestamps of the stages (seconds)
+    import time as _time
+
+    def mark(what):
+        if trace is not None:
+            trace.append((what, _time.perf_counter()))
+
+    mark("enter")
     world = dist.get_world_size(group) if group is not None else 1
     rank = dist.get_rank(group) if group is not None else 0
     numel = {op.dst: int(torch.Size(shapes[op.dst]).numel()) for op in ops}
@@ -129,6 +137,7 @@ def _run_elementwise(ops, lookup, shapes, device, out_device, group=None, stats=
             if not in_place(t):
                 staged.append((i, j, in_total, t))
                 in_total += _round_up(t.numel())
+    mark("scanned")
     arena_in = torch.empty(max(in_total, 1), dtype=torch.float32, device=device)
     arena_out = torch.empty(max(shard_size[rank], 1), dtype=torch.float32, device=device)
     staged_at = {(i, j): off for i, j, off, _ in staged}
@@ -164,31 +173,58 @@ def _run_elementwise(ops, lookup, shapes, device, out_device, group=None, stats=
     bounds = [len(mine) * g // ngroups for g in range(ngroups + 1)]
     h2d_stream = torch.cuda.Stream(device) if pipelined else cur
     d2h_stream = torch.cuda.Stream(device) if pipelined else cur
+    mark("arenas")
     host = torch.empty(max(shard_size[rank], 1), dtype=torch.float32, pin_memory=True) if pipelined else None
+    mark("pinned output")
     if pipelined:
         h2d_stream.wait_stream(cur)
         d2h_stream.wait_stream(cur)
     h2d = 0
     plans = []
     try:
+        # 1. every group's host -> device copies go out first (asynchronous, one vlm_copy_batch per group, an event
+        #    after each): the DMA engine starts at once and the segment tables below are built while it runs.
+        #    (Measured on the B200 box, tools/pcie_probe.py + tools/merge_trace.py: 680 MB in + 340 MB out take 13.5 ms
+        #    as two big copies running at once, 19.1 ms one after the other; this call takes 19.6 ms — 0.8 ms of host
+        #    preparation, 15.6 ms until the last of the ~390 input copies has landed, 2 ms of tail.)
+        ready = []
+        for g in range(ngroups):
+            idx = mine[bounds[g]: bounds[g + 1]]
+            with torch.cuda.stream(h2d_stream):
+                batch = []     # contiguous fp32 sources: one call for the whole group
+                for i in idx:
+                    for _, _, off, t in staged_by_op.get(i, ()):
+                        src = t.detach()
+                        h2d += src.numel() * 4 if not t.is_cuda else 0
+                        if src.dtype == torch.float32 and src.is_contiguous():
+                            keep.append(src)
+                            batch.append((off * 4, src.data_ptr(), src.numel() * 4))
+                            continue
+                        src = src.reshape(-1)
+                        if src.dtype != torch.float32:
+                            src = src.float()
+                        arena_in[off: off + src.numel()].copy_(src, non_blocking=True)
+                if batch:
+                    nb = len(batch)
+                    offs = (ctypes.c_uint64 * nb)(*[b[0] for b in batch])
+                    srcs = (ctypes.c_void_p * nb)(*[b[1] for b in batch])
+                    sizes = (ctypes.c_uint64 * nb)(*[b[2] for b in batch])
+                    _lib.check(lib.vlm_copy_batch(arena_in.data_ptr(), offs, srcs, sizes, nb, h2d_stream.cuda_stream))
+                ev = torch.cuda.Event()
+                ev.record(h2d_stream)
+                ready.append(ev)
+        mark("h2d enqueued")
+        # 2. per group: segment table, kernel as soon as the group's inputs have landed, device -> host copy of its
+        #    outputs on a third stream (PCIe is full duplex)
         for g in range(ngroups):
             idx = mine[bounds[g]: bounds[g + 1]]
             if not idx:
                 continue
-            with torch.cuda.stream(h2d_stream):
-                for i in idx:
-                    for _, _, off, t in staged_by_op.get(i, ()):
-                        src = t.detach().reshape(-1)
-                        if src.dtype != torch.float32:
-                            src = src.float()
-                        arena_in[off: off + src.numel()].copy_(src, non_blocking=True)
-                        h2d += src.numel() * 4 if not t.is_cuda else 0
             segs = (_lib.MergeSeg * len(idx))(*[make_seg(i) for i in idx])
             plan = ctypes.c_void_p()
             _lib.check(lib.vlm_merge_plan_create(segs, len(idx), ctypes.byref(plan)))
             plans.append(plan)
-            if pipelined:
-                cur.wait_stream(h2d_stream)
+            cur.wait_event(ready[g])
             _lib.check(lib.vlm_merge_plan_run(plan, cur.cuda_stream))
             if stats is not None:
                 stats["merge_bytes"] = stats.get("merge_bytes", 0) + int(lib.vlm_merge_plan_bytes(plan))
@@ -198,14 +234,18 @@ def _run_elementwise(ops, lookup, shapes, device, out_device, group=None, stats=
                 d2h_stream.wait_stream(cur)
                 with torch.cuda.stream(d2h_stream):
                     host[lo:hi].copy_(arena_out[lo:hi], non_blocking=True)
+        mark("all enqueued")
     finally:
         cur.synchronize()
+        mark("kernels done")
         if pipelined:
             h2d_stream.synchronize()
             d2h_stream.synchronize()
         for plan in plans:
-            lib.vlm_merge_plan_destroy(plan)
+            if plan:
+                lib.vlm_merge_plan_destroy(plan)
 
+    mark("copies done")
     # all-gather of the merged shards (the path's one exchange step)
     full = layout.gather(arena_out, rank, group)
     if pipelined:
