@@ -61,7 +61,9 @@ using namespace vlm;
 extern "C" int vlm_sym_pack_upper(const float* g, int d, int64_t ldg, float* packed, void* stream) {
   VLM_REQUIRE(g != nullptr && packed != nullptr && d > 0 && ldg >= d, VLM_ERR_INVALID_ARG,
               "vlm_sym_pack_upper: bad arguments");
-  const int blocks = std::min(148 * 8, (d + 7) / 8);
+  int nsm = 0;
+  if (int rc = device_sm_count(&nsm)) return rc;
+  const int blocks = std::min(nsm * 8, (d + 7) / 8);
   sym_pack_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, d, ldg, packed);
   VLM_CUDA(cudaGetLastError());
   count_launch();
