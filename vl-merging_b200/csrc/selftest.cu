@@ -7,7 +7,10 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <cmath>
+#include <functional>
+#include <utility>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -422,6 +425,73 @@ static void syrk_batch_case(int n1, int64_t rows1, int d1, int n2, int64_t rows2
   }
 }
 
+
+// Fused similarity + top-10 (vlm_sim_topk) against a host computation: m x n scores of fp16 features, ten best
+// columns per row (ties: lower column first).
+static void simtopk_case(int m, int n, int d, int iters) {
+  std::vector<__half> ha((size_t)m * d), hb((size_t)n * d);
+  for (auto& v : ha) v = __float2half(frand());
+  for (auto& v : hb) v = __float2half(frand());
+  __half *da, *db;
+  CK(cudaMalloc(&da, ha.size() * 2));
+  CK(cudaMalloc(&db, hb.size() * 2));
+  CK(cudaMemcpy(da, ha.data(), ha.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(db, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice));
+  const int splits = vlm_sim_topk_splits(m, n);
+  float* dv;
+  int* di;
+  CK(cudaMalloc(&dv, (size_t)m * splits * 10 * 4));
+  CK(cudaMalloc(&di, (size_t)m * splits * 10 * 4));
+  VK(vlm_sim_topk(da, m, d, db, n, d, d, VLM_F16, dv, di, splits, nullptr));
+  CK(cudaDeviceSynchronize());
+  std::vector<float> hv((size_t)m * splits * 10);
+  std::vector<int> hi((size_t)m * splits * 10);
+  CK(cudaMemcpy(hv.data(), dv, hv.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hi.data(), di, hi.size() * 4, cudaMemcpyDeviceToHost));
+  int bad = 0;
+  const int rows_checked = std::min(m, 64);
+  std::vector<double> sc(n);
+  for (int r = 0; r < rows_checked; ++r) {
+    const int row = (int)(((int64_t)r * 2654435761ll) % m);
+    for (int c = 0; c < n; ++c) {
+      double acc = 0;
+      for (int k = 0; k < d; ++k) acc += (double)__half2float(ha[(size_t)row * d + k]) * __half2float(hb[(size_t)c * d + k]);
+      sc[c] = acc;
+    }
+    // merge the split lists of this row, then compare with the host's top-k by SCORE (fp32 accumulation may swap near-ties)
+    std::vector<std::pair<float, int>> got;
+    for (int t = 0; t < splits * 10; ++t)
+      if (hi[((size_t)row * splits) * 10 + t] >= 0) got.push_back({hv[((size_t)row * splits) * 10 + t], hi[((size_t)row * splits) * 10 + t]});
+    std::stable_sort(got.begin(), got.end(), [](auto& a, auto& b) { return a.first > b.first; });
+    std::vector<double> want(sc);
+    std::sort(want.begin(), want.end(), std::greater<double>());
+    const int k = std::min(10, n);
+    if ((int)got.size() < k) {
+      ++bad;
+      continue;
+    }
+    for (int t = 0; t < k; ++t) {
+      const int c = got[t].second;
+      if (c < 0 || c >= n || fabs(sc[c] - want[t]) > 1e-3 * sqrt((double)d) || fabs(got[t].first - sc[c]) > 1e-3 * sqrt((double)d)) ++bad;
+    }
+  }
+  float ms = 0;
+  if (iters > 0) {
+    Timer t;
+    VK(vlm_sim_topk(da, m, d, db, n, d, d, VLM_F16, dv, di, splits, nullptr));
+    t.start();
+    for (int i = 0; i < iters; ++i) VK(vlm_sim_topk(da, m, d, db, n, d, d, VLM_F16, dv, di, splits, nullptr));
+    ms = t.stop() / iters;
+  }
+  printf("SIMTOPK m=%-6d n=%-6d d=%-5d splits=%d mismatches=%d  %.3f ms  %.1f TFLOP/s  %s\n", m, n, d, splits, bad, ms,
+         ms > 0 ? 2.0 * m * n * d / ms * 1e-9 : 0.0, bad == 0 ? "OK" : "FAIL");
+  if (bad) ++g_fail;
+  CK(cudaFree(da));
+  CK(cudaFree(db));
+  CK(cudaFree(dv));
+  CK(cudaFree(di));
+}
+
 // Row-sliced activation: the view h[:, off:off+seg_rows] of an (nseg, n_tok, d) tensor, read in place
 // (vlm_syrk_accum_strided, and the same problem through vlm_syrk_accum_batch) against a host fp64 Gram of the
 // slice (host_ref) or the contiguous kernel on a packed copy of the slice.
@@ -757,6 +827,10 @@ int main(int argc, char** argv) {
     else syrk_case<__half>("case f16", VLM_F16, rows, d, mode, false, iters, 1e-4);
     return g_fail;
   }
+  if (argc >= 6 && !strcmp(argv[1], "simtopk")) {  // selftest simtopk <m> <n> <d> <iters>
+    simtopk_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]));
+    return g_fail;
+  }
   if (argc >= 9 && !strcmp(argv[1], "batch")) {  // selftest batch <n1> <rows1> <d1> <n2> <rows2> <d2> <iters>
     syrk_batch_case(atoi(argv[2]), atoll(argv[3]), atoi(argv[4]), atoi(argv[5]), atoll(argv[6]), atoi(argv[7]), atoi(argv[8]));
     return g_fail;
@@ -842,6 +916,10 @@ int main(int argc, char** argv) {
   syrk_strided_case<float>("f32 d=200 (gen-1 path)", VLM_F32, 3, 50, 7, 33, 200, true, 0, 2e-3);
   syrk_strided_case<float>("f32 image slice x64", VLM_F32, 64, 617, 40, 577, 768, false, 20, 2e-4);
   syrk_strided_case<float>("f32 text slice x64", VLM_F32, 64, 617, 0, 40, 768, false, 20, 2e-4);
+
+  // retrieval step: fused similarity + top-10
+  simtopk_case(130, 300, 192, 0);
+  simtopk_case(5000, 25000, 768, 5);
 
   // grouped launches: a small mixed group for correctness
   syrk_batch_case(3, 1000, 768, 2, 333, 256, 0);
