@@ -92,7 +92,7 @@ _lib = None
 
 def build(verbose=False):
     """Compile libvlmerge.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    res = subprocess.run(["make", "-C", CSRC_DIR, "all"], capture_output=True, text=True)
+    res = subprocess.run(["make", "-C", CSRC_DIR, f"-j{min(8, os.cpu_count() or 1)}", "all"], capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout[-4000:])
         print(res.stderr[-4000:])
