@@ -339,6 +339,8 @@ int solve_ctx(cudaStream_t st, size_t want_elems, SolveCtx* out) {
     it = g_cs_ctx.emplace(key, c).first;
   }
   SolveCtx& c = it->second;
+  // re-bind on every use: a stream that was destroyed and re-created may come back with the same handle value
+  VLM_REQUIRE(g_cs.set_stream(c.h, st) == 0, VLM_ERR_DRIVER, "cusolverDnSetStream failed");
   if (c.work_elems < want_elems) {
     // the old buffer may still be in use by work queued on `st`: free it in stream order, allocate the new one now
     if (c.work) VLM_CUDA(cudaFreeAsync(c.work, st));
