@@ -778,6 +778,8 @@ def bench_regmean_chain(vlm, model, cfg, cache, dev, step, dev_batches, B):
     layers = sorted({0, L - 1})
     c64 = vlm.GramCache(dev, precision="fp64")
     c64.register(model, use_moe=True)
+    ci8 = vlm.GramCache(dev, precision="int8x4")
+    ci8.register(model, use_moe=True)
     ref, mods = {}, dict(model.named_modules())
     names = [f"transformer.blocks.{i}.{t}" for i in layers for m in ("v", "l")
              for t in (f"attn.{m}", f"attn.{m}.proj", f"mlp.{m}.fc1", f"mlp.{m}.fc2")]
@@ -795,12 +797,13 @@ def bench_regmean_chain(vlm, model, cfg, cache, dev, step, dev_batches, B):
         h.remove()
     sd = {k: v.detach() for k, v in model.state_dict().items()}
     out = {}
-    worst = {"fp64": 0.0, "tf32": 0.0}
+    worst = {"fp64": 0.0, "int8x4": 0.0, "tf32": 0.0}
     detail = {}
     for alpha in (1.0, 0.9):
         mcfg = dict(vlffn_start_layer_index=cfg["vlffn_start_layer_index"], scaling_for_non_diag=alpha,
                     loss_names={"irtr": 1, "vqa": 0, "nlvr2": 0})
         merged = {"fp64": vlm.regmean(sd, mcfg, device=dev, num_layers=L, gram_matrices=c64),
+                  "int8x4": vlm.regmean(sd, mcfg, device=dev, num_layers=L, gram_matrices=ci8),
                   "tf32": vlm.regmean(sd, mcfg, device=dev, num_layers=L, gram_matrices=cache)}
         for i in layers:
             for tgt, wk, gk in ((f"transformer.blocks.{i}.attn.qkv.weight", "transformer.blocks.{i}.attn.{m}.qkv.weight", "transformer.blocks.{i}.attn.{m}"),
@@ -819,22 +822,26 @@ def bench_regmean_chain(vlm, model, cfg, cache, dev, step, dev_batches, B):
                     worst[mode] = max(worst[mode], e)
                     detail[f"{mode} a={alpha} {tgt.split('blocks.')[1]}"] = float(f"{e:.3e}")
     out["e2e_rel_err_vs_fp64_grams"] = worst["fp64"]
+    out["e2e_rel_err_vs_fp64_grams_int8x4"] = worst["int8x4"]
     out["e2e_rel_err_vs_fp64_grams_single_pass_tf32"] = worst["tf32"]
     out["e2e_detail"] = detail
     out["e2e_note"] = ("whole chain on identical activations: hooks -> device Grams -> regmean vs the reference formula on the "
                        "reference hook's fp64 Grams; worst of 8 linears (layers 0 and L-1) x scaling_for_non_diag in {1.0, 0.9}. "
-                       "e2e_rel_err_vs_fp64_grams = GramCache(precision='fp64') (the RegMean-grade mode, BASELINE 1e-4); "
+                       "e2e_rel_err_vs_fp64_grams = GramCache(precision='fp64') (the RegMean-grade mode, BASELINE 1e-4); _int8x4 = the same "
+                       "grade from the integer tensor cores (exact int8 digit-plane products); "
                        "single_pass_tf32 = the default fast mode (Gram tolerance 1e-3)")
     gram_err = max(float(((c64.gram(n) - g).norm() / g.norm()).item()) for n, g in ref.items())
     out["fp64_mode_gram_rel_fro"] = gram_err
+    out["int8x4_mode_gram_rel_fro"] = max(float(((ci8.gram(n) - g).norm() / g.norm()).item()) for n, g in ref.items())
 
     # calibration throughput of the precision modes (same forward, same batches; CUDA events, 3 steps each)
     cache.enabled = False
     modes = {}
     c3 = vlm.GramCache(dev, precision="tf32x3", defer_bytes=cache.defer_bytes, max_pending_bytes=cache.max_pending_bytes)
     c3.register(model, use_moe=True)
-    for mode, c, other in (("fp64", c64, c3), ("tf32x3", c3, c64)):
-        other.enabled, c.enabled = False, True
+    for mode, c in (("fp64", c64), ("int8x4", ci8), ("tf32x3", c3)):
+        for other in (c64, ci8, c3):
+            other.enabled = other is c
         c.reset()
         step(dev_batches[0])
         torch.cuda.synchronize(dev)
@@ -847,8 +854,9 @@ def bench_regmean_chain(vlm, model, cfg, cache, dev, step, dev_batches, B):
         modes[mode] = {"value": round(3 * B / (a.elapsed_time(b) * 1e-3), 2), "unit": "samples/s",
                        "ms_per_step": round(a.elapsed_time(b) / 3, 2)}
     c64.remove_hooks()
+    ci8.remove_hooks()
     c3.remove_hooks()
-    del c64, c3
+    del c64, ci8, c3
     cache.enabled = True
     cache.reset()
     out["gram_precision_modes"] = modes

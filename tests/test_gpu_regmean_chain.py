@@ -32,6 +32,7 @@ def chain():
     model = vlm.init_synthetic_(vlm.VLMo(cfg).eval(), seed=1).cuda()
     caches = {
         "fp64": vlm.GramCache(precision="fp64"),
+        "int8x4": vlm.GramCache(precision="int8x4"),
         "tf32": vlm.GramCache(),
         "tf32x3": vlm.GramCache(precision="tf32x3"),
         "tf32x3_grouped": vlm.GramCache(precision="tf32x3", defer_bytes=64 << 20),
@@ -79,6 +80,15 @@ def test_fp64_gram_equals_reference_hook(chain):
         assert g.dtype == torch.float64 and g.device.type == "cpu" and torch.equal(g, g.T)
 
 
+def test_int8_gram_error(chain):
+    """Integer tensor cores: exact products and sums of the quantised activations; what is left is the 2^-27
+    quantisation against the column maximum and the dropped digit products (< 2^-26)."""
+    cfg, sd, np_sd, caches, ref, np_ref = chain
+    assert all(caches["int8x4"].gram(k).dtype == torch.float64 for k in ref)
+    worst = max(((caches["int8x4"].gram(k) - g).norm() / g.norm()).item() for k, g in ref.items())
+    assert worst < 1e-7, worst
+
+
 @pytest.mark.parametrize("mode", ["tf32x3", "tf32x3_grouped"])
 def test_split_gram_error(chain, mode):
     """Gram error of the split mode: what is left is the tensor core's truncating fp32 accumulation (a near-uniform
@@ -102,7 +112,7 @@ def _regmean_errors(chain, mode, alpha):
 
 
 @pytest.mark.parametrize("alpha", [1.0, 0.9])
-@pytest.mark.parametrize("mode", ["fp64"])
+@pytest.mark.parametrize("mode", ["fp64", "int8x4"])
 def test_regmean_chain_within_1e4_of_fp64_gram_oracle(chain, mode, alpha):
     import oracle
 

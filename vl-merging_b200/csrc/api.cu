@@ -183,6 +183,30 @@ extern "C" int vlm_tf32_split(const float* x, int64_t rows, int d, int64_t ldx, 
   return tf32_split_launch(x, rows, d, ldx, seg_rows, seg_stride, out, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" uint64_t vlm_syrk_i8x4_scratch_bytes(int64_t rows, int d) {
+  return (rows > 0 && d > 0) ? (uint64_t)syrk_i8x4_scratch_bytes(rows, d) : 0;
+}
+
+extern "C" int vlm_syrk_accum_i8x4(const float* x, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
+                                   void* scratch, uint64_t scratch_bytes, double* g, int64_t ldg, void* stream) {
+  VLM_REQUIRE(rows >= 0 && d > 0 && g != nullptr && ldg >= d && (rows == 0 || (x != nullptr && ldx >= d)),
+              VLM_ERR_INVALID_ARG, "vlm_syrk_accum_i8x4: bad arguments (rows=%lld d=%d)", (long long)rows, d);
+  VLM_REQUIRE(d % 128 == 0, VLM_ERR_UNSUPPORTED,
+              "vlm_syrk_accum_i8x4: d must be a multiple of 128 (got %d); use vlm_syrk_accum_f64", d);
+  VLM_REQUIRE(seg_rows >= 0 && seg_stride >= 0 && (seg_rows == 0 || rows % seg_rows == 0), VLM_ERR_INVALID_ARG,
+              "vlm_syrk_accum_i8x4: rows (%lld) must be a multiple of seg_rows (%lld)", (long long)rows, (long long)seg_rows);
+  VLM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ldx & 3) == 0 && (seg_stride & 3) == 0 &&
+                  (reinterpret_cast<uintptr_t>(scratch) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 7) == 0,
+              VLM_ERR_ALIGNMENT, "vlm_syrk_accum_i8x4: x / scratch must be 16-byte aligned, ldx and seg_stride multiples of 4");
+  VLM_REQUIRE(rows < ((int64_t)1 << 31), VLM_ERR_INVALID_ARG, "vlm_syrk_accum_i8x4: rows too large");
+  if (rows == 0) return 0;
+  VLM_REQUIRE(scratch != nullptr && scratch_bytes >= syrk_i8x4_scratch_bytes(rows, d), VLM_ERR_INVALID_ARG,
+              "vlm_syrk_accum_i8x4: scratch too small (%llu bytes, need %llu)", (unsigned long long)scratch_bytes,
+              (unsigned long long)syrk_i8x4_scratch_bytes(rows, d));
+  if (int rc = require_sm100()) return rc;
+  return syrk_i8x4_launch(x, rows, d, ldx, seg_rows, seg_stride, scratch, g, ldg, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int vlm_sym_finalize(float* g, int d, int64_t ldg, double* out_f64, int64_t ld64, void* stream) {
   VLM_REQUIRE(g != nullptr && d > 0 && ldg >= d, VLM_ERR_INVALID_ARG, "vlm_sym_finalize: bad arguments");
   VLM_REQUIRE(out_f64 == nullptr || ld64 >= d, VLM_ERR_INVALID_ARG, "vlm_sym_finalize: ld64 < d");

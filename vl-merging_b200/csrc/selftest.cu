@@ -228,6 +228,7 @@ static void syrk_case(const char* name, int dtype, int64_t rows, int d, int mode
 }
 
 
+
 // Split-precision Gram (vlm_tf32_split + VLM_TF32X2): host fp64 Gram of the whole matrix (host_ref) or of 12
 // sample rows; optionally a row-segmented source (nseg > 1: rows = nseg * seg_rows out of n_tok-row items).
 static void syrk_split_case(const char* name, int nseg, int n_tok, int off, int seg_rows, int d, int mode, bool host_ref,
@@ -364,6 +365,80 @@ static void syrk_f64_case(const char* name, int dtype, int nseg, int n_tok, int 
   CK(cudaFree(dx));
   CK(cudaFree(g));
 }
+
+
+// Exact Gram on the integer tensor cores (vlm_syrk_accum_i8x4): host fp64 Gram of the whole matrix (host_ref) or of 12 sample rows;
+// optionally a row-segmented source.  Two accumulating calls (checks "+=" and the split-K reduction), then the mirror.
+static void syrk_i8_case(const char* name, int nseg, int n_tok, int off, int seg_rows, int d, int mode,
+                          bool host_ref, int iters, double tol) {
+  typedef float T;
+  std::vector<T> hx((size_t)nseg * n_tok * d);
+  fill_x<T>(hx, mode);
+  const int64_t rows = (int64_t)nseg * seg_rows;
+  T* dx;
+  double* g;
+  CK(cudaMalloc(&dx, hx.size() * sizeof(T)));
+  CK(cudaMalloc(&g, (size_t)d * d * 8));
+  void* scratch;
+  const uint64_t sbytes = vlm_syrk_i8x4_scratch_bytes(rows, d);
+  CK(cudaMalloc(&scratch, sbytes));
+  CK(cudaMemcpy(dx, hx.data(), hx.size() * sizeof(T), cudaMemcpyHostToDevice));
+  CK(cudaMemset(g, 0, (size_t)d * d * 8));
+  const T* slice = dx + (size_t)off * d;
+  auto xrow = [&](int64_t k) { return &hx[(((size_t)(k / seg_rows)) * n_tok + off + (k % seg_rows)) * d]; };
+  std::vector<int> rs;
+  if (host_ref) for (int r = 0; r < d; ++r) rs.push_back(r);
+  else for (int t = 0; t < 12; ++t) rs.push_back((int)(((int64_t)t * 2654435761ll + 17) % d));
+  std::vector<double> ref((size_t)d * d, 0.0);
+  for (int r : rs) {
+    double* o = &ref[(size_t)r * d];
+    for (int c = 0; c < d; ++c) o[c] = 0;
+    for (int64_t k = 0; k < rows; ++k) {
+      const T* xr = xrow(k);
+      const double a = to_d(xr[r]);
+      for (int c = r; c < d; ++c) o[c] += a * to_d(xr[c]);
+    }
+  }
+  const int64_t sr = nseg > 1 ? seg_rows : 0;
+  VK(vlm_syrk_accum_i8x4(slice, rows, d, d, sr, (int64_t)n_tok * d, scratch, sbytes, g, d, nullptr));
+  VK(vlm_syrk_accum_i8x4(slice, rows, d, d, sr, (int64_t)n_tok * d, scratch, sbytes, g, d, nullptr));
+  VK(vlm_sym_finalize_f64(g, d, d, nullptr));
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("I8X4  %-27s KERNEL FAILED: %s\n", name, cudaGetErrorString(e));
+    exit(97);
+  }
+  std::vector<double> out((size_t)d * d);
+  CK(cudaMemcpy(out.data(), g, out.size() * 8, cudaMemcpyDeviceToHost));
+  double num = 0, den = 0;
+  size_t asym = 0;
+  for (int r : rs)
+    for (int c = r; c < d; ++c) {
+      const double want = 2.0 * ref[(size_t)r * d + c];
+      const double df = out[(size_t)r * d + c] - want;
+      num += df * df;
+      den += want * want;
+      asym += out[(size_t)c * d + r] != out[(size_t)r * d + c];
+    }
+  const double err = sqrt(num / den);
+  float ms = 0;
+  if (iters > 0) {
+    Timer t;
+    VK(vlm_syrk_accum_i8x4(slice, rows, d, d, sr, (int64_t)n_tok * d, scratch, sbytes, g, d, nullptr));
+    t.start();
+    for (int i = 0; i < iters; ++i) VK(vlm_syrk_accum_i8x4(slice, rows, d, d, sr, (int64_t)n_tok * d, scratch, sbytes, g, d, nullptr));
+    ms = t.stop() / iters;
+  }
+  const double flops = (double)rows * d * (d + 1.0);
+  const bool ok = err <= tol && asym == 0 && std::isfinite(err);
+  printf("I8X4  %-27s rows=%-6lld d=%-5d relF=%.3e asym=%zu  %.3f ms  %.2f TFLOP/s(sym)  %s\n", name, (long long)rows, d, err,
+         asym, ms, ms > 0 ? flops / ms * 1e-9 : 0.0, ok ? "OK" : "FAIL");
+  if (!ok) ++g_fail;
+  CK(cudaFree(dx));
+  CK(cudaFree(g));
+  CK(cudaFree(scratch));
+}
+
 
 
 // Grouped launch of n1 problems (rows1 x d1) + n2 problems (rows2 x d2), all fp32, distinct activations and Grams:
@@ -835,6 +910,11 @@ int main(int argc, char** argv) {
     syrk_batch_case(atoi(argv[2]), atoll(argv[3]), atoi(argv[4]), atoi(argv[5]), atoll(argv[6]), atoi(argv[7]), atoi(argv[8]));
     return g_fail;
   }
+  if (argc >= 5 && !strcmp(argv[1], "i8x4")) {  // selftest i8x4 <rows> <d> <iters> [positive]
+    const int rows = atoi(argv[2]), d = atoi(argv[3]), iters = atoi(argv[4]), mode = argc > 5 ? atoi(argv[5]) : 0;
+    syrk_i8_case("case f32", 1, rows, 0, rows, d, mode, false, iters, 1e-7);
+    return g_fail;
+  }
   if (argc >= 6 && !strcmp(argv[1], "f64")) {  // selftest f64 <f32|bf16> <rows> <d> <iters> [positive]
     const int rows = atoi(argv[3]), d = atoi(argv[4]), iters = atoi(argv[5]), mode = argc > 6 ? atoi(argv[6]) : 0;
     if (!strcmp(argv[2], "f32")) syrk_f64_case<float>("case f32", VLM_F32, 1, rows, 0, rows, d, mode, false, iters, 1e-13);
@@ -899,6 +979,15 @@ int main(int argc, char** argv) {
   syrk_f64_case<float>("f32 text d=768", VLM_F32, 1, 2560, 0, 2560, 768, 0, false, 20, 1e-13);
   syrk_f64_case<float>("f32 image d=768", VLM_F32, 1, 36928, 0, 36928, 768, 0, false, 10, 1e-13);
   syrk_f64_case<float>("f32 image d=3072", VLM_F32, 1, 36928, 0, 36928, 3072, 1, false, 3, 1e-13);
+
+  // exact Gram on the integer tensor cores
+  syrk_i8_case("i8x4 1 tile", 1, 64, 0, 64, 128, 0, true, 0, 1e-7);
+  syrk_i8_case("i8x4 d=768 ragged rows", 1, 1000, 0, 1000, 768, 0, true, 0, 1e-7);
+  syrk_i8_case("i8x4 d=384 positive", 1, 333, 0, 333, 384, 1, true, 0, 1e-7);
+  syrk_i8_case("i8x4 image slice", 4, 617, 40, 577, 768, 0, true, 0, 1e-7);
+  syrk_i8_case("i8x4 text d=3072", 1, 2560, 0, 2560, 3072, 1, false, 10, 1e-7);
+  syrk_i8_case("i8x4 image d=768", 1, 36928, 0, 36928, 768, 0, false, 10, 1e-7);
+  syrk_i8_case("i8x4 image d=3072", 1, 36928, 0, 36928, 3072, 1, false, 5, 1e-7);
 
   // split precision (3xTF32)
   syrk_split_case("tf32x3 1 tile", 1, 64, 0, 64, 128, 0, true, 0, 2e-6);

@@ -77,6 +77,7 @@ __device__ __forceinline__ void tensormap_acquire(const CUtensorMap* tm) {
 }  // namespace vlm
 
 #include "syrk_2sm.cuh"
+#include "syrk_i8.cuh"
 
 namespace vlm {
 namespace {
@@ -215,11 +216,12 @@ PairKernel pick_kernel(int dtype) {
 // shares 672 TFLOP/s (many short segments whose 128 KB epilogues cannot hide), this schedule 753-758; an L2
 // look-ahead prefetch (cp.async.bulk.prefetch.tensor) cost 8 %, half-height stages x 8 cost 14 %.  (Numbers of the
 // multicast pair kernel of round 1; the cta_group::2 kernel keeps the schedule unchanged.)
-void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairSeg>* segs, std::vector<int>* off) {
+void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairSeg>* segs, std::vector<int>* off,
+                         int64_t seg_cap_arg) {
   // chunks per accumulation: 4096 fp32 rows / 8192 16-bit rows.  Measured on the B200 with all-positive
   // activations 36928 x 3072: cap 128 / 256 / 512 / none -> rel. error 7.6e-4 / 7.8e-4 / 8.2e-4 / 1.0e-3 (fp32),
   // 2.2e-5 / 5.0e-5 / 8.8e-5 (bf16), at 742 / 753 / 766 / 779 TFLOP/s.
-  int64_t seg_cap = 128;
+  int64_t seg_cap = seg_cap_arg > 0 ? seg_cap_arg : 128;
   if (const char* e = getenv("VLM_SYRK_SEG_CHUNKS")) seg_cap = std::max(1, atoi(e));
   const int nsb = (d + 255) / 256;
   struct T {
@@ -393,6 +395,83 @@ int tf32_split_launch(const float* x, int64_t rows, int d, int64_t ldx, int64_t 
   const int64_t n4 = rows * (d / 4);
   const int64_t blocks = std::min<int64_t>((n4 + 255) / 256, (int64_t)nsm * 8);
   tf32_split_kernel<<<(unsigned)std::max<int64_t>(1, blocks), 256, 0, stream>>>(x, rows, d, ldx, seg_rows, seg_stride, out);
+  VLM_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// Exact Gram on the integer tensor cores (syrk_i8.cuh).  scratch: [4 planes: 4 * rows * d bytes][exps: d ints]
+// [column maxima: d uints], 16-byte aligned.
+size_t syrk_i8x4_scratch_bytes(int64_t rows, int d) { return (size_t)4 * rows * d + (size_t)8 * d + 64; }
+
+int syrk_i8x4_launch(const float* x, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride, void* scratch,
+                     double* g, int64_t ldg, cudaStream_t stream) {
+  int dev = 0, nsm = 0;
+  VLM_CUDA(cudaGetDevice(&dev));
+  if (int rc = device_sm_count(&nsm)) return rc;
+  if (int rc = ensure_encode()) return rc;
+  if (seg_rows >= rows) seg_rows = 0;
+  int8_t* planes = static_cast<int8_t*>(scratch);
+  int* exps = reinterpret_cast<int*>(planes + (((size_t)4 * rows * d + 15) & ~(size_t)15));
+  unsigned* amax = reinterpret_cast<unsigned*>(exps + d);
+  // pre-pass: column maxima -> exponents -> digit planes
+  VLM_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned) * d, stream));
+  const int64_t slabs = std::max<int64_t>(1, std::min<int64_t>((rows + 255) / 256, (int64_t)nsm * 16 / std::max(1, d / 128)));
+  const int64_t rps = (rows + slabs - 1) / slabs;
+  i8_colmax_kernel<<<dim3((unsigned)(d / 128), (unsigned)((rows + rps - 1) / rps)), 256, 0, stream>>>(
+      x, rows, d, ldx, seg_rows, seg_stride, rps, amax);
+  i8_exps_kernel<<<(d + 255) / 256, 256, 0, stream>>>(amax, d, exps);
+  const int64_t n4 = rows * (d / 4);
+  i8_slice_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((n4 + 255) / 256, (int64_t)nsm * 16)), 256, 0, stream>>>(
+      x, rows, d, ldx, seg_rows, seg_stride, exps, planes);
+  VLM_CUDA(cudaGetLastError());
+  count_launch(3);
+
+  // three views of the planes: 32 rows of all four (groups 4, 3), 32 rows of planes 0..2 (groups 2, 1), 128 rows of
+  // plane 0 (group 0)
+  CUtensorMap tm_p[3];
+  for (int ph = 0; ph < 3; ++ph) {
+    const cuuint32_t np = ph == 0 ? 4 : ph == 1 ? 3 : 1;
+    cuuint64_t gdim[4] = {128, (cuuint64_t)rows, (cuuint64_t)(d / 128), np};
+    cuuint64_t gstr[3] = {(cuuint64_t)d, 128, (cuuint64_t)rows * d};
+    cuuint32_t box[4] = {128, (cuuint32_t)(ph == 2 ? 128 : 32), 1, np};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode2(&tm_p[ph], CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, planes, gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VLM_REQUIRE(r == CUDA_SUCCESS, VLM_ERR_DRIVER, "cuTensorMapEncodeTiled(int8 planes) failed: CUresult %d", (int)r);
+  }
+  const int64_t kc = (rows + 31) / 32;
+  VLM_REQUIRE(kc < (int64_t)1 << 30, VLM_ERR_INVALID_ARG, "vlm_syrk_accum_i8x4: too many row chunks");
+  std::lock_guard<std::mutex> lk(g_mu2);
+  auto key = std::make_tuple(dev, kc, d, -8, nsm);   // bk = -8: the int8 schedule (every segment once per phase)
+  auto it = g_sched2.find(key);
+  if (it == g_sched2.end()) {
+    std::vector<PairSeg> base, segs;
+    std::vector<int> boff, off(1, 0);
+    // int32 accumulation of a four-pair group is exact for 2^17 rows (|digit| <= 64); 2048 chunks = 65536 rows per
+    // segment keeps the epilogues (64K fp64 adds per CTA) rare
+    build_pair_schedule(kc, d, nsm / 2, &base, &boff, 2048);
+    for (size_t c = 0; c + 1 < boff.size(); ++c) {
+      for (int i = boff[c]; i < boff[c + 1]; ++i)
+        for (int ph = 0; ph < kI8Phases; ++ph) segs.push_back({base[i].sa, base[i].sb | (ph << 16), base[i].k0, base[i].k1});
+      off.push_back((int)segs.size());
+    }
+    DeviceSchedule2 ds;
+    ds.nclusters = (int)off.size() - 1;
+    VLM_CUDA(cudaMalloc(&ds.d_segs, std::max<size_t>(1, segs.size()) * sizeof(PairSeg)));
+    VLM_CUDA(cudaMalloc(&ds.d_off, off.size() * sizeof(int)));
+    VLM_CUDA(cudaMemcpyAsync(ds.d_segs, segs.data(), segs.size() * sizeof(PairSeg), cudaMemcpyHostToDevice, stream));
+    VLM_CUDA(cudaMemcpyAsync(ds.d_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    VLM_CUDA(cudaStreamSynchronize(stream));
+    it = g_sched2.emplace(key, ds).first;
+  }
+  const DeviceSchedule2& sched = it->second;
+  const int smem = kI8SmemBytes;
+  VLM_CUDA(cudaFuncSetAttribute(syrk_i8x4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  I8Args args{g, ldg, exps};
+  syrk_i8x4_kernel<<<2 * sched.nclusters, kThreads, smem, stream>>>(tm_p[0], tm_p[1], tm_p[2], sched.d_segs, sched.d_off, d,
+                                                                    args);
   VLM_CUDA(cudaGetLastError());
   count_launch();
   return 0;

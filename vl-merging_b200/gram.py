@@ -126,6 +126,10 @@ class GramCache:
         "fp64": the reference's own arithmetic — fp64 products, fp64 accumulation, fp64 Gram buffers
         (vlm_syrk_accum_f64, DMMA tensor cores); the mode that carries regmean to its 1e-4 tolerance.  Launches
         immediately (no grouping).
+        "int8x4": the same RegMean-grade fp64 Grams from the INTEGER tensor cores — every fp32 column is scaled by a
+        power of two and cut into four int8 digit planes, whose products accumulate exactly in int32
+        (vlm_syrk_accum_i8x4; Gram error ~1e-8, regmean within 1e-4 like "fp64") at about a third of the cost; small
+        problems, 16-bit activations and widths that are not multiples of 128 take the fp64 path.
         defer_bytes > 0: an activation of at most that many bytes is not launched on its own (the Gram of a
         40-token text batch is launch-bound: ~7 us of fixed cost for ~2 us of tensor-core work, and a 768-wide
         image Gram exposes its prologue and final epilogue); the hook keeps a REFERENCE to it (no copy) and
@@ -148,10 +152,10 @@ class GramCache:
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self._lib = _lib.lib()
-        if precision not in ("tf32", "tf32x3", "fp64"):
-            raise ValueError(f"precision must be 'tf32', 'tf32x3' or 'fp64' (got {precision!r})")
+        if precision not in ("tf32", "tf32x3", "fp64", "int8x4"):
+            raise ValueError(f"precision must be 'tf32', 'tf32x3', 'fp64' or 'int8x4' (got {precision!r})")
         self.precision = precision
-        self.dtype = torch.float64 if precision == "fp64" else torch.float32   # of the Gram buffers
+        self.dtype = torch.float64 if precision in ("fp64", "int8x4") else torch.float32   # of the Gram buffers
         self._planes = None    # scratch for the {hi, lo} planes of the split mode (grown on demand, reused in stream order)
         self._fn = self._lib.vlm_syrk_accum_simt if use_simt else self._lib.vlm_syrk_accum
         self.buffers = {}       # name -> fp32 [d, d] (upper triangle authoritative until finalize())
@@ -219,7 +223,14 @@ class GramCache:
         self._finalized = False
         code = _DTYPES[keep.dtype]
         nbytes = rows * ldx * elem
-        if self.precision == "fp64":
+        if self.precision == "int8x4" and code == _lib.VLM_F32 and d % 128 == 0 and rows * d >= (1 << 22) \
+                and ptr % 16 == 0 and ldx % 4 == 0 and seg_stride % 4 == 0:
+            nbytes = int(self._lib.vlm_syrk_i8x4_scratch_bytes(rows, d))
+            scratch = self._plane_scratch((nbytes + 3) // 4)
+            _lib.check(self._lib.vlm_syrk_accum_i8x4(ptr, rows, d, ldx, seg_rows, seg_stride, scratch.data_ptr(), nbytes,
+                                                     g.data_ptr(), g.stride(0), self._launch_stream(keep)))
+            return
+        if self.dtype == torch.float64:
             _lib.check(self._lib.vlm_syrk_accum_f64(ptr, code, rows, d, ldx, seg_rows, seg_stride,
                                                     g.data_ptr(), g.stride(0), self._launch_stream(keep)))
             return
