@@ -36,7 +36,8 @@ namespace {
 constexpr int kI8PlaneBytes = 32 * 128;   // 32 rows x 128 int8 columns
 constexpr int kI8Planes = 4;
 constexpr int kI8Phases = 3;              // {groups 4, 3}, {groups 2, 1}, {group 0}
-constexpr int kI8SmemBytes = k2Stages * k2StageBytes + 1280 + 4 * 32 * 33 * 4 + 1024;   // stages, barriers, 4 transpose tiles
+constexpr int kI8SlabBytes = 16384;         // 128 rows x 16 fp64 columns: one TMA reduce-add box, or the 4 transpose tiles
+constexpr int kI8SmemBytes = k2Stages * k2StageBytes + kI8SlabBytes + 1280 + 1024;   // stages, slab, barriers
 
 struct I8Args {
   double* g;
@@ -61,10 +62,32 @@ __device__ __forceinline__ void umma2_i8(uint32_t d_tmem, uint64_t adesc, uint64
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// 2^e as a double, from its exponent bits (|e| < 1022: column exponents come from fp32 maxima)
+__device__ __forceinline__ double i8_pow2(int e) { return __hiloint2double((1023 + e) << 20, 0); }
+
 // segs: PairSeg with the phase (0: groups 4 and 3, 1: groups 2 and 1, 2: group 0) in bits 16.. of sb; k in 32-row chunks
+// TMA_EPI: the epilogue leaves through fp64 TMA reduce-adds (tm_g: G as a 2-D fp64 tensor, box 16 columns x 128 rows);
+// otherwise through per-element red.global.add.f64
+template <bool TMA_EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 syrk_i8x4_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__ CUtensorMap tm_p1,
-                 const __grid_constant__ CUtensorMap tm_p2, const PairSeg* __restrict__ segs,
+                 const __grid_constant__ CUtensorMap tm_p2, const __grid_constant__ CUtensorMap tm_g,
+                 const PairSeg* __restrict__ segs,
                  const int* __restrict__ seg_off, int d, const __grid_constant__ I8Args args) {
   constexpr int kBlk = kBlockBytes;       // one operand of a stage
   constexpr int kNS = k2Stages;
@@ -72,7 +95,8 @@ syrk_i8x4_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kNS * kStageB);
+  uint8_t* slab = smem + kNS * kStageB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slab + kI8SlabBytes);
   uint64_t* full = bars;                  // used in the leader only
   uint64_t* empty = bars + kNS;
   uint64_t* tfull = bars + 2 * kNS;
@@ -90,6 +114,7 @@ syrk_i8x4_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constan
     tma_prefetch_desc(&tm_p0);
     tma_prefetch_desc(&tm_p1);
     tma_prefetch_desc(&tm_p2);
+    if (TMA_EPI) tma_prefetch_desc(&tm_g);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kNS; ++i) {
@@ -198,14 +223,80 @@ syrk_i8x4_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constan
       acc_phase ^= 1;
     }
   } else if (warp >= 4) {
-    // ===== epilogue (both CTAs): exact int32 sums of the two groups -> scaled fp64 adds into G =====
+    if constexpr (TMA_EPI) {
+      // ===== epilogue (both CTAs): exact int32 sums of the phase's groups -> scaled fp64 -> TMA reduce-add into G =====
+      // The two groups of a phase differ by 2^7 in scale: acc1 * 128 + acc0 is exact in 64-bit integers (< 2^39) and in
+      // fp64, so a phase adds ONE double per element.  Scaling is by powers of two only (2^(E_row - 10 - 7 grp) and
+      // 2^(E_col), built from their exponent bits).  Thread `row` writes 16 doubles of its accumulator row into a
+      // 128-byte-swizzled slab; one cp.reduce.async.bulk.tensor (.add, fp64) per 128 x 16 slab carries it into G — the
+      // per-element red.global.add.f64 of the first version ran at the SM's ~0.8 atomics per clock (22 us per phase).
+      const int q = warp - 4;
+      const int epi_tid = threadIdx.x - 128;
+      const int row = q * 32 + lane;
+      uint32_t acc_phase = 0;
+      const uint32_t tempty0 = mapa_rank(smem_u32(tempty), 0);
+      const uint32_t rbase = smem_u32(slab) + row * 128;
+      for (int s = seg_begin; s < seg_end; ++s) {
+        const PairSeg seg = segs[s];
+        const int sb_t = seg.sb & 0xFFFF, ph = seg.sb >> 16;
+        const bool diag = seg.sa == sb_t;
+        const int n_off = (diag && rank == 1) ? 1 : 0;   // peer on a diagonal tile: only block (2a+1, 2a+1)
+        const int row0 = (2 * seg.sa + (int)rank) * 128;
+        const int col0 = (2 * sb_t + n_off) * 128;
+        const int grp = 4 - 2 * ph;                      // the group in accumulator 0 (the smaller scale of the phase)
+        const bool two = ph != 2;
+        mbar_wait(tfull, acc_phase);
+        tc_fence_after();
+        const double rscale = (row0 + row < d) ? i8_pow2(__ldg(args.exps + row0 + row) - 10 - 7 * grp) : 0.0;
+        const int nslab = (row0 < d) ? min(8 * (2 - n_off), (d - col0 + 15) / 16) : 0;
+        for (int sl = 0; sl < nslab; ++sl) {
+          uint32_t v[16], w[16];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + n_off * 128 + sl * 16;
+          tmem_ld_32x32b_x16(taddr, v);
+          if (two) tmem_ld_32x32b_x16(taddr + kAccCols, w);
+          const int c0 = col0 + sl * 16;
+          double val[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) val[j] = (c0 + j < d) ? i8_pow2(__ldg(args.exps + c0 + j)) * rscale : 0.0;
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const long long c = two ? (long long)(int)w[j] * 128 + (int)v[j] : (long long)(int)v[j];
+            val[j] *= __ll2double_rn(c);
+          }
+          if (epi_tid == 0) bulk_wait_group_read<0>();   // the previous slab has left shared memory
+          named_bar_sync(1, 128);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t addr = rbase + ((uint32_t)(c ^ (row & 7)) << 4);
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(val[2 * c]), "d"(val[2 * c + 1]) : "memory");
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (epi_tid == 0) {
+            tma_reduce_add_2d(&tm_g, slab, c0, row0);
+            bulk_commit_group();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty0);
+        acc_phase ^= 1;
+      }
+      if (epi_tid == 0) bulk_wait_group_read<0>();
+    } else {
+    // ===== epilogue (both CTAs): exact int32 sums of the phase's groups -> ONE scaled fp64 add per element =====
+    // The two groups of a phase differ by 2^7 in scale: acc1 * 128 + acc0 is exact in 64-bit integers (< 2^39) and in
+    // fp64, so a phase costs one red.global.add.f64 per element, not two.  Scaling is by powers of two only: the row
+    // thread multiplies by 2^(E_row - 10 - 7 grp), the column lane by 2^(E_col), both built from their exponent bits.
     // A thread owns one accumulator ROW, so adding straight from its registers would touch 32 rows of G per warp
-    // instruction.  Each warp transposes its 32 x 32 chunk through shared memory and lane j adds column j of all 32
-    // rows: one contiguous 256-byte red.global.add.f64 per instruction.
+    // instruction.  Each warp transposes 32 rows x 16 columns of doubles through shared memory; lane l then adds
+    // column (l & 15) of rows 2 i + (l >> 4): two contiguous 128-byte runs per instruction.
     const int q = warp - 4;
-    int* tile = reinterpret_cast<int*>(smem + kNS * kStageB + 1280) + q * (32 * 33);
+    double* tile = reinterpret_cast<double*>(slab) + q * (32 * 17);
     uint32_t acc_phase = 0;
     const uint32_t tempty0 = mapa_rank(smem_u32(tempty), 0);
+    const int lc = lane & 15, lr = lane >> 4;
     for (int s = seg_begin; s < seg_end; ++s) {
       const PairSeg seg = segs[s];
       const int sb_t = seg.sb & 0xFFFF, ph = seg.sb >> 16;
@@ -213,27 +304,33 @@ syrk_i8x4_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constan
       const int n_off = (diag && rank == 1) ? 1 : 0;   // peer on a diagonal tile: only block (2a+1, 2a+1)
       const int row_base = (2 * seg.sa + (int)rank) * 128 + q * 32;
       const int col0 = (2 * sb_t + n_off) * 128;
+      const int grp = 4 - 2 * ph;                      // the group in accumulator 0 (the smaller scale of the phase)
+      const bool two = ph != 2;
       mbar_wait(tfull, acc_phase);
       tc_fence_after();
-      const int e_lane = (row_base + lane < d) ? __ldg(args.exps + row_base + lane) - 10 : 0;
-      const int nchunk = min(4 * (2 - n_off), (d - col0 + 31) / 32);
-      for (int which = 0; which < (ph == 2 ? 1 : 2); ++which) {
-        const int grp = 4 - 2 * ph - which;            // accumulator 0: the higher group of the phase
-        for (int ch = 0; ch < nchunk; ++ch) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + which * kAccCols + n_off * 128 + ch * 32, v);
-          tmem_ld_wait();
+      const double rscale = (row_base + lane < d) ? i8_pow2(__ldg(args.exps + row_base + lane) - 10 - 7 * grp) : 0.0;
+      const int nchunk = (row_base < d) ? min(4 * (2 - n_off), (d - col0 + 31) / 32) : 0;
+      for (int ch = 0; ch < nchunk; ++ch) {
+        uint32_t v[32], w[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + n_off * 128 + ch * 32;
+        tmem_ld_32x32b_x32(taddr, v);
+        if (two) tmem_ld_32x32b_x32(taddr + kAccCols, w);
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = (int)v[j];
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const long long c = two ? (long long)(int)w[16 * h + j] * 128 + (int)v[16 * h + j] : (long long)(int)v[16 * h + j];
+            tile[lane * 17 + j] = __ll2double_rn(c) * rscale;
+          }
           __syncwarp();
-          const int c = col0 + ch * 32 + lane;
-          const int e_col = (c < d ? __ldg(args.exps + c) : 0) - 7 * grp;
+          const int c = col0 + ch * 32 + 16 * h + lc;
+          const double cscale = c < d ? i8_pow2(__ldg(args.exps + c)) : 0.0;
+          double* gp = args.g + (int64_t)(row_base + lr) * args.ldg + c;
 #pragma unroll 4
-          for (int r = 0; r < 32; ++r) {
-            const int iv = tile[r * 33 + lane];
-            const int e_row = __shfl_sync(0xffffffffu, e_lane, r);
-            if (row_base + r < d && c < d && iv != 0)
-              atomicAdd(args.g + (int64_t)(row_base + r) * args.ldg + c, ldexp((double)iv, e_row + e_col));
+          for (int i = 0; i < 16; ++i) {
+            const double val = tile[(2 * i + lr) * 17 + lc] * cscale;
+            if (row_base + 2 * i + lr < d && val != 0.0) atomicAdd(gp + (int64_t)(2 * i) * args.ldg, val);
           }
           __syncwarp();
         }
@@ -242,6 +339,7 @@ syrk_i8x4_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty0);
       acc_phase ^= 1;
+    }
     }
   }
 
@@ -256,64 +354,93 @@ __device__ __forceinline__ const float* i8_row_ptr(const float* x, int64_t r, in
   return seg_rows > 0 ? x + (r / seg_rows) * seg_stride + (r % seg_rows) * ldx : x + r * ldx;
 }
 
-// grid (d / 128, row slabs); thread t of 32 x 8: columns 4 (t & 31) .. +3 of the block, rows (t >> 5) + 8 i of the slab
+// grid (d / 128, row slabs); thread t of 32 x 8: columns 4 (t & 31) .. +3 of the block, rows (t >> 5) + 8 i of the slab;
+// four independent 16-byte loads in flight per thread (the pass is a pure HBM stream)
 __global__ void __launch_bounds__(256) i8_colmax_kernel(const float* __restrict__ x, int64_t rows, int d, int64_t ldx,
                                                         int64_t seg_rows, int64_t seg_stride, int64_t rows_per_slab,
                                                         unsigned* __restrict__ amax_bits) {
   const int c = blockIdx.x * 128 + (threadIdx.x & 31) * 4;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_slab, r1 = min(rows, r0 + rows_per_slab);
   float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
-  for (int64_t r = r0 + (threadIdx.x >> 5); r < r1; r += 8) {
+  int64_t r = r0 + (threadIdx.x >> 5);
+  for (; r + 24 < r1; r += 32) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      v[u] = __ldg(reinterpret_cast<const float4*>(i8_row_ptr(x, r + 8 * u, ldx, seg_rows, seg_stride) + c));
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      m0 = fmaxf(m0, fabsf(v[u].x)), m1 = fmaxf(m1, fabsf(v[u].y)), m2 = fmaxf(m2, fabsf(v[u].z)), m3 = fmaxf(m3, fabsf(v[u].w));
+  }
+  for (; r < r1; r += 8) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(i8_row_ptr(x, r, ldx, seg_rows, seg_stride) + c));
     m0 = fmaxf(m0, fabsf(v.x)), m1 = fmaxf(m1, fabsf(v.y)), m2 = fmaxf(m2, fabsf(v.z)), m3 = fmaxf(m3, fabsf(v.w));
   }
-  // non-negative floats order like their bit patterns
-  atomicMax(amax_bits + c, __float_as_uint(m0));
-  atomicMax(amax_bits + c + 1, __float_as_uint(m1));
-  atomicMax(amax_bits + c + 2, __float_as_uint(m2));
-  atomicMax(amax_bits + c + 3, __float_as_uint(m3));
+  // the block's 8 row groups are combined in shared memory first: one atomic per column per block (with one per
+  // thread, ~1000 same-address atomics per column serialised in L2 and took longer than the pass over X)
+  __shared__ float4 red[8][32];
+  red[threadIdx.x >> 5][threadIdx.x & 31] = make_float4(m0, m1, m2, m3);
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const float* col = reinterpret_cast<const float*>(&red[0][0]) + threadIdx.x;
+    float m = col[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, col[w * 128]);
+    atomicMax(amax_bits + blockIdx.x * 128 + threadIdx.x, __float_as_uint(m));   // non-negative floats order like their bit patterns
+  }
 }
 
-__global__ void i8_exps_kernel(const unsigned* __restrict__ amax_bits, int d, int* __restrict__ exps) {
+// E_c with 2^E_c > max |x[:, c]| (clamped below so that 2^(26 - E_c) is a finite float), and that scale as a float,
+// written over the column maximum it was derived from
+__global__ void i8_exps_kernel(unsigned* __restrict__ amax_bits_then_scales, int d, int* __restrict__ exps) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= d) return;
-  const float m = __uint_as_float(amax_bits[c]);
-  exps[c] = (m > 0.f && isfinite(m)) ? ilogbf(m) + 1 : 0;     // 2^E > m
+  const float m = __uint_as_float(amax_bits_then_scales[c]);
+  const int e = (m > 0.f && isfinite(m)) ? max(ilogbf(m) + 1, -100) : 0;
+  exps[c] = e;
+  amax_bits_then_scales[c] = (unsigned)(127 + 26 - e) << 23;   // the float 2^(26 - e)
 }
 
-__device__ __forceinline__ void i8_digits(float x, int e, int8_t (&dg)[4]) {
-  int t = __float2int_rn(ldexpf(x, 26 - e));   // |t| < 2^26 (+1 from rounding at the very top)
-#pragma unroll
-  for (int p = 3; p > 0; --p) {
-    const int r = ((t + 64) & 127) - 64;       // balanced digit in [-64, 63]
-    dg[p] = (int8_t)r;
-    t = (t - r) >> 7;
-  }
-  dg[0] = (int8_t)t;                           // |t| <= 33
+// Four values of one row -> one char4 per digit plane.  t = rint(x * 2^(26 - E)), |t| <= 2^26; with the bias
+// 64 (1 + 2^7 + 2^14) added, the plain base-128 digits of u are the balanced digits of t plus 64 (and u >> 21 is the
+// top digit itself), so the four planes are bit fields of u: shifts, byte permutes and a per-byte "- 64".
+__device__ __forceinline__ unsigned i8_pack_low_bytes(unsigned a0, unsigned a1, unsigned a2, unsigned a3) {
+  return __byte_perm(__byte_perm(a0, a1, 0x0040), __byte_perm(a2, a3, 0x0040), 0x5410);
 }
-
-// one thread: 4 consecutive columns of one row -> a char4 in each of the four planes ([plane][row][d])
-__global__ void __launch_bounds__(256) i8_slice_kernel(const float* __restrict__ x, int64_t rows, int d, int64_t ldx,
+__device__ __forceinline__ unsigned i8_minus64_per_byte(unsigned w) {   // bytes in [0, 127] -> two's complement of (byte - 64)
+  w = (w & 0x7f7f7f7fu) ^ 0x40404040u;
+  return w | ((w & 0x40404040u) << 1);
+}
+__device__ __forceinline__ void i8_slice_store(const float4& v, const float4& sc, int8_t* __restrict__ dst, int64_t plane) {
+  constexpr int kBias = 64 * (1 + 128 + 128 * 128);
+  const unsigned u0 = (unsigned)(__float2int_rn(v.x * sc.x) + kBias), u1 = (unsigned)(__float2int_rn(v.y * sc.y) + kBias);
+  const unsigned u2 = (unsigned)(__float2int_rn(v.z * sc.z) + kBias), u3 = (unsigned)(__float2int_rn(v.w * sc.w) + kBias);
+  *reinterpret_cast<unsigned*>(dst + 3 * plane) = i8_minus64_per_byte(i8_pack_low_bytes(u0, u1, u2, u3));
+  *reinterpret_cast<unsigned*>(dst + 2 * plane) = i8_minus64_per_byte(i8_pack_low_bytes(u0 >> 7, u1 >> 7, u2 >> 7, u3 >> 7));
+  *reinterpret_cast<unsigned*>(dst + 1 * plane) = i8_minus64_per_byte(i8_pack_low_bytes(u0 >> 14, u1 >> 14, u2 >> 14, u3 >> 14));
+  *reinterpret_cast<unsigned*>(dst) = i8_pack_low_bytes((unsigned)((int)u0 >> 21), (unsigned)((int)u1 >> 21),
+                                                         (unsigned)((int)u2 >> 21), (unsigned)((int)u3 >> 21));
+}
+// block b: rows b, b + gridDim.x, ... (four rows per trip); thread t: column quads t, t + 256, ... of each row — no
+// index division, 4 x 16 bytes in flight per thread
+__global__ void __launch_bounds__(256, 4) i8_slice_kernel(const float* __restrict__ x, int64_t rows, int d, int64_t ldx,
                                                        int64_t seg_rows, int64_t seg_stride,
-                                                       const int* __restrict__ exps, int8_t* __restrict__ planes) {
+                                                       const float* __restrict__ scales, int8_t* __restrict__ planes) {
   const int d4 = d >> 2;
-  const int64_t n4 = rows * d4;
   const int64_t plane = rows * (int64_t)d;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / d4;
-    const int c = (int)(i - r * d4) * 4;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(i8_row_ptr(x, r, ldx, seg_rows, seg_stride) + c));
-    const int4 e = __ldg(reinterpret_cast<const int4*>(exps + c));
-    int8_t a[4], b[4], cc[4], dd[4];
-    i8_digits(v.x, e.x, a);
-    i8_digits(v.y, e.y, b);
-    i8_digits(v.z, e.z, cc);
-    i8_digits(v.w, e.w, dd);
+  const int64_t G = gridDim.x;
+  for (int64_t r0 = blockIdx.x; r0 < rows; r0 += 4 * G) {
+    const float* src[4];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      char4 o;
-      o.x = a[p], o.y = b[p], o.z = cc[p], o.w = dd[p];
-      *reinterpret_cast<char4*>(planes + p * plane + r * d + c) = o;
+    for (int u = 0; u < 4; ++u) src[u] = i8_row_ptr(x, min(r0 + u * G, rows - 1), ldx, seg_rows, seg_stride);
+    for (int cq = threadIdx.x; cq < d4; cq += 256) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(src[u]) + cq);
+      const float4 e = __ldg(reinterpret_cast<const float4*>(scales) + cq);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r0 + u * G < rows) i8_slice_store(v[u], e, planes + (r0 + u * G) * d + 4 * cq, plane);
     }
   }
 }

@@ -421,9 +421,8 @@ int syrk_i8x4_launch(const float* x, int64_t rows, int d, int64_t ldx, int64_t s
   i8_colmax_kernel<<<dim3((unsigned)(d / 128), (unsigned)((rows + rps - 1) / rps)), 256, 0, stream>>>(
       x, rows, d, ldx, seg_rows, seg_stride, rps, amax);
   i8_exps_kernel<<<(d + 255) / 256, 256, 0, stream>>>(amax, d, exps);
-  const int64_t n4 = rows * (d / 4);
-  i8_slice_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((n4 + 255) / 256, (int64_t)nsm * 16)), 256, 0, stream>>>(
-      x, rows, d, ldx, seg_rows, seg_stride, exps, planes);
+  i8_slice_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>(rows, (int64_t)nsm * 4)), 256, 0, stream>>>(
+      x, rows, d, ldx, seg_rows, seg_stride, reinterpret_cast<const float*>(amax), planes);
   VLM_CUDA(cudaGetLastError());
   count_launch(3);
 
@@ -440,6 +439,17 @@ int syrk_i8x4_launch(const float* x, int64_t rows, int d, int64_t ldx, int64_t s
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VLM_REQUIRE(r == CUDA_SUCCESS, VLM_ERR_DRIVER, "cuTensorMapEncodeTiled(int8 planes) failed: CUresult %d", (int)r);
+  }
+  // G as a 2-D fp64 tensor for the epilogue's TMA reduce-adds: box = 16 columns (128 bytes) x 128 rows
+  CUtensorMap tm_g;
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)d};
+    cuuint64_t gstr[1] = {(cuuint64_t)ldg * 8};
+    cuuint32_t box[2] = {16, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode2(&tm_g, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, g, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VLM_REQUIRE(r == CUDA_SUCCESS, VLM_ERR_DRIVER, "cuTensorMapEncodeTiled(G fp64) failed: CUresult %d", (int)r);
   }
   const int64_t kc = (rows + 31) / 32;
   VLM_REQUIRE(kc < (int64_t)1 << 30, VLM_ERR_INVALID_ARG, "vlm_syrk_accum_i8x4: too many row chunks");
@@ -468,10 +478,14 @@ int syrk_i8x4_launch(const float* x, int64_t rows, int d, int64_t ldx, int64_t s
   }
   const DeviceSchedule2& sched = it->second;
   const int smem = kI8SmemBytes;
-  VLM_CUDA(cudaFuncSetAttribute(syrk_i8x4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  static const bool tma_epi = [] {
+    const char* e = getenv("VLM_I8_TMA_EPILOGUE");
+    return e ? atoi(e) != 0 : true;
+  }();
+  auto kernel = tma_epi ? syrk_i8x4_kernel<true> : syrk_i8x4_kernel<false>;
+  VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   I8Args args{g, ldg, exps};
-  syrk_i8x4_kernel<<<2 * sched.nclusters, kThreads, smem, stream>>>(tm_p[0], tm_p[1], tm_p[2], sched.d_segs, sched.d_off, d,
-                                                                    args);
+  kernel<<<2 * sched.nclusters, kThreads, smem, stream>>>(tm_p[0], tm_p[1], tm_p[2], tm_g, sched.d_segs, sched.d_off, d, args);
   VLM_CUDA(cudaGetLastError());
   count_launch();
   return 0;
