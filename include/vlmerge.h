@@ -83,16 +83,18 @@ int vlm_syrk_accum_f64(const void* x, int dtype, int64_t rows, int d, int64_t ld
                        int64_t seg_stride, double* g, int64_t ldg, void* stream);
 int vlm_sym_finalize_f64(double* g, int d, int64_t ldg, void* stream);
 
-/* The same Gram, exact, on the INTEGER tensor cores: each fp32 column is scaled by a power of two above its maximum
- * in this call and every value becomes four balanced int8 digits (q = rint(x * 2^(26-E_c)) = sum D_p * 128^(3-p));
- * the ten digit-plane products with p + q <= 3 run as tcgen05.mma kind::i8 (int32 accumulation: exact) and are added
- * to the fp64 Gram with their power-of-two scales.  Error: 2^-27 of the column maximum per element (unbiased
- * quantisation) + the dropped products (< 2^-26 of sqrt(G_ii G_jj)) — measured 1e-8, RegMean-grade — at about 3x the
- * cost of the single TF32 pass instead of the fp64 path's 25x.  x: fp32, 16-byte aligned, optionally row-segmented;
- * d % 128 == 0 (VLM_ERR_UNSUPPORTED otherwise: use vlm_syrk_accum_f64); scratch: vlm_syrk_i8x4_scratch_bytes(rows, d)
- * bytes of device memory, 16-byte aligned, borrowed for the call.  G as for vlm_syrk_accum_f64. */
+/* The same Gram, exact, on the INTEGER tensor cores: each column is scaled by a power of two above its maximum in
+ * this call and every value becomes four balanced int8 digits (q = rint(x * 2^(26-E_c)) = sum D_p * 128^(3-p));
+ * the thirteen digit-plane products with p + q <= 4 run as tcgen05.mma kind::i8 (int32 accumulation: exact) and are
+ * added to the fp64 Gram with their power-of-two scales (fp64 TMA reduce-adds).  Error: 2^-27 of the column maximum
+ * per element (unbiased quantisation) + the dropped products (< 1e-9 of sqrt(G_ii G_jj)) — measured 1e-10 on normal
+ * data, 3e-9 on LayerNorm outputs: RegMean-grade — at about 3.5x the cost of the single TF32 pass instead of the fp64
+ * path's 28x.  x: VLM_F32 / VLM_F16 / VLM_BF16 (16-bit values are widened exactly), 16-byte aligned, ldx % 4 == 0,
+ * optionally row-segmented; d % 128 == 0 (VLM_ERR_UNSUPPORTED otherwise: use vlm_syrk_accum_f64); scratch:
+ * vlm_syrk_i8x4_scratch_bytes(rows, d) bytes of device memory, 16-byte aligned, borrowed for the call.  G as for
+ * vlm_syrk_accum_f64, 16-byte aligned with an even ldg (TMA). */
 uint64_t vlm_syrk_i8x4_scratch_bytes(int64_t rows, int d);
-int vlm_syrk_accum_i8x4(const float* x, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
+int vlm_syrk_accum_i8x4(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
                         void* scratch, uint64_t scratch_bytes, double* g, int64_t ldg, void* stream);
 
 /* Several independent vlm_syrk_accum problems of the same dtype in ONE launch (e.g. the 48 small Grams of the

@@ -180,6 +180,8 @@ def test_precision_modes_match_the_fp64_hook(precision):
     xs = {"plain": torch.randn(3, 577, 256, device="cuda", generator=gen), "slice": joint[:, 40:],
           "big": torch.randn(64, 577, 256, device="cuda", generator=gen) * torch.linspace(0.01, 30, 256, device="cuda"),
           "bigslice": joint64[:, 40:],
+          "big_f16": (torch.randn(64, 577, 256, device="cuda", generator=gen) * torch.linspace(0.01, 30, 256, device="cuda")).half(),
+          "bigslice_bf16": joint64.bfloat16()[:, 40:],         # int8x4 takes 16-bit activations too (widened exactly)
           "text": joint[:, :40], "bf16": torch.randn(1000, 128, device="cuda", generator=gen).bfloat16(),
           "odd": torch.randn(333, 200, device="cuda", generator=gen)}
     tol = {"fp64": 2e-13, "int8x4": 1e-7, "tf32x3": 5e-6}[precision]
@@ -197,7 +199,7 @@ def test_precision_modes_match_the_fp64_hook(precision):
             g = cache.gram(name)
             assert g.dtype == (torch.float32 if precision == "tf32x3" else torch.float64)
             err = ((g.double() - ref).norm() / ref.norm()).item()
-            if precision == "tf32x3" and name in ("bf16", "big", "bigslice"):
+            if precision == "tf32x3" and name in ("bf16", "big", "bigslice", "big_f16", "bigslice_bf16"):
                 tol_here = 5e-5      # what is left there is the tensor core's truncating fp32 accumulation (rows x 2^-25)
             else:
                 tol_here = tol

@@ -60,8 +60,8 @@ SIGNATURES = {
     "vlm_syrk_accum_f64": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64,
                                    c_void_p]),
     "vlm_syrk_i8x4_scratch_bytes": (c_uint64, [c_int64, c_int]),
-    "vlm_syrk_accum_i8x4": (c_int, [c_void_p, c_int64, c_int, c_int64, c_int64, c_int64, c_void_p, c_uint64, c_void_p,
-                                    c_int64, c_void_p]),
+    "vlm_syrk_accum_i8x4": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_int64, c_int64, c_void_p, c_uint64,
+                                    c_void_p, c_int64, c_void_p]),
     "vlm_sym_finalize_f64": (c_int, [c_void_p, c_int, c_int64, c_void_p]),
     "vlm_syrk_accum_batch": (c_int, [POINTER(SyrkProblem), c_int, c_int, c_void_p]),
     "vlm_syrk_accum_strided": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_int64, c_int64, c_void_p, c_int64,

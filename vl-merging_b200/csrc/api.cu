@@ -187,8 +187,11 @@ extern "C" uint64_t vlm_syrk_i8x4_scratch_bytes(int64_t rows, int d) {
   return (rows > 0 && d > 0) ? (uint64_t)syrk_i8x4_scratch_bytes(rows, d) : 0;
 }
 
-extern "C" int vlm_syrk_accum_i8x4(const float* x, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
-                                   void* scratch, uint64_t scratch_bytes, double* g, int64_t ldg, void* stream) {
+extern "C" int vlm_syrk_accum_i8x4(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows,
+                                   int64_t seg_stride, void* scratch, uint64_t scratch_bytes, double* g, int64_t ldg,
+                                   void* stream) {
+  VLM_REQUIRE(dtype == VLM_F32 || dtype == VLM_F16 || dtype == VLM_BF16, VLM_ERR_INVALID_ARG,
+              "vlm_syrk_accum_i8x4: dtype must be VLM_F32, VLM_F16 or VLM_BF16 (got %d)", dtype);
   VLM_REQUIRE(rows >= 0 && d > 0 && g != nullptr && ldg >= d && (rows == 0 || (x != nullptr && ldx >= d)),
               VLM_ERR_INVALID_ARG, "vlm_syrk_accum_i8x4: bad arguments (rows=%lld d=%d)", (long long)rows, d);
   VLM_REQUIRE(d % 128 == 0, VLM_ERR_UNSUPPORTED,
@@ -196,15 +199,17 @@ extern "C" int vlm_syrk_accum_i8x4(const float* x, int64_t rows, int d, int64_t 
   VLM_REQUIRE(seg_rows >= 0 && seg_stride >= 0 && (seg_rows == 0 || rows % seg_rows == 0), VLM_ERR_INVALID_ARG,
               "vlm_syrk_accum_i8x4: rows (%lld) must be a multiple of seg_rows (%lld)", (long long)rows, (long long)seg_rows);
   VLM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ldx & 3) == 0 && (seg_stride & 3) == 0 &&
-                  (reinterpret_cast<uintptr_t>(scratch) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 7) == 0,
-              VLM_ERR_ALIGNMENT, "vlm_syrk_accum_i8x4: x / scratch must be 16-byte aligned, ldx and seg_stride multiples of 4");
+                  (reinterpret_cast<uintptr_t>(scratch) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 &&
+                  (ldg & 1) == 0,
+              VLM_ERR_ALIGNMENT,
+              "vlm_syrk_accum_i8x4: x / scratch / g must be 16-byte aligned, ldx and seg_stride multiples of 4, ldg even");
   VLM_REQUIRE(rows < ((int64_t)1 << 31), VLM_ERR_INVALID_ARG, "vlm_syrk_accum_i8x4: rows too large");
   if (rows == 0) return 0;
   VLM_REQUIRE(scratch != nullptr && scratch_bytes >= syrk_i8x4_scratch_bytes(rows, d), VLM_ERR_INVALID_ARG,
               "vlm_syrk_accum_i8x4: scratch too small (%llu bytes, need %llu)", (unsigned long long)scratch_bytes,
               (unsigned long long)syrk_i8x4_scratch_bytes(rows, d));
   if (int rc = require_sm100()) return rc;
-  return syrk_i8x4_launch(x, rows, d, ldx, seg_rows, seg_stride, scratch, g, ldg, static_cast<cudaStream_t>(stream));
+  return syrk_i8x4_launch(x, dtype, rows, d, ldx, seg_rows, seg_stride, scratch, g, ldg, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vlm_sym_finalize(float* g, int d, int64_t ldg, double* out_f64, int64_t ld64, void* stream) {

@@ -369,9 +369,9 @@ static void syrk_f64_case(const char* name, int dtype, int nseg, int n_tok, int 
 
 // Exact Gram on the integer tensor cores (vlm_syrk_accum_i8x4): host fp64 Gram of the whole matrix (host_ref) or of 12 sample rows;
 // optionally a row-segmented source.  Two accumulating calls (checks "+=" and the split-K reduction), then the mirror.
-static void syrk_i8_case(const char* name, int nseg, int n_tok, int off, int seg_rows, int d, int mode,
+template <typename T>
+static void syrk_i8_case(const char* name, int dtype, int nseg, int n_tok, int off, int seg_rows, int d, int mode,
                           bool host_ref, int iters, double tol) {
-  typedef float T;
   std::vector<T> hx((size_t)nseg * n_tok * d);
   fill_x<T>(hx, mode);
   const int64_t rows = (int64_t)nseg * seg_rows;
@@ -400,8 +400,8 @@ static void syrk_i8_case(const char* name, int nseg, int n_tok, int off, int seg
     }
   }
   const int64_t sr = nseg > 1 ? seg_rows : 0;
-  VK(vlm_syrk_accum_i8x4(slice, rows, d, d, sr, (int64_t)n_tok * d, scratch, sbytes, g, d, nullptr));
-  VK(vlm_syrk_accum_i8x4(slice, rows, d, d, sr, (int64_t)n_tok * d, scratch, sbytes, g, d, nullptr));
+  VK(vlm_syrk_accum_i8x4(slice, dtype, rows, d, d, sr, (int64_t)n_tok * d, scratch, sbytes, g, d, nullptr));
+  VK(vlm_syrk_accum_i8x4(slice, dtype, rows, d, d, sr, (int64_t)n_tok * d, scratch, sbytes, g, d, nullptr));
   VK(vlm_sym_finalize_f64(g, d, d, nullptr));
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
@@ -424,9 +424,9 @@ static void syrk_i8_case(const char* name, int nseg, int n_tok, int off, int seg
   float ms = 0;
   if (iters > 0) {
     Timer t;
-    VK(vlm_syrk_accum_i8x4(slice, rows, d, d, sr, (int64_t)n_tok * d, scratch, sbytes, g, d, nullptr));
+    VK(vlm_syrk_accum_i8x4(slice, dtype, rows, d, d, sr, (int64_t)n_tok * d, scratch, sbytes, g, d, nullptr));
     t.start();
-    for (int i = 0; i < iters; ++i) VK(vlm_syrk_accum_i8x4(slice, rows, d, d, sr, (int64_t)n_tok * d, scratch, sbytes, g, d, nullptr));
+    for (int i = 0; i < iters; ++i) VK(vlm_syrk_accum_i8x4(slice, dtype, rows, d, d, sr, (int64_t)n_tok * d, scratch, sbytes, g, d, nullptr));
     ms = t.stop() / iters;
   }
   const double flops = (double)rows * d * (d + 1.0);
@@ -910,9 +910,12 @@ int main(int argc, char** argv) {
     syrk_batch_case(atoi(argv[2]), atoll(argv[3]), atoi(argv[4]), atoi(argv[5]), atoll(argv[6]), atoi(argv[7]), atoi(argv[8]));
     return g_fail;
   }
-  if (argc >= 5 && !strcmp(argv[1], "i8x4")) {  // selftest i8x4 <rows> <d> <iters> [positive]
+  if (argc >= 5 && !strcmp(argv[1], "i8x4")) {  // selftest i8x4 <rows> <d> <iters> [positive] [f32|f16|bf16]
     const int rows = atoi(argv[2]), d = atoi(argv[3]), iters = atoi(argv[4]), mode = argc > 5 ? atoi(argv[5]) : 0;
-    syrk_i8_case("case f32", 1, rows, 0, rows, d, mode, false, iters, 1e-7);
+    const char* dt = argc > 6 ? argv[6] : "f32";
+    if (!strcmp(dt, "f16")) syrk_i8_case<__half>("case f16", VLM_F16, 1, rows, 0, rows, d, mode, false, iters, 1e-7);
+    else if (!strcmp(dt, "bf16")) syrk_i8_case<__nv_bfloat16>("case bf16", VLM_BF16, 1, rows, 0, rows, d, mode, false, iters, 1e-7);
+    else syrk_i8_case<float>("case f32", VLM_F32, 1, rows, 0, rows, d, mode, false, iters, 1e-7);
     return g_fail;
   }
   if (argc >= 6 && !strcmp(argv[1], "f64")) {  // selftest f64 <f32|bf16> <rows> <d> <iters> [positive]
@@ -981,13 +984,15 @@ int main(int argc, char** argv) {
   syrk_f64_case<float>("f32 image d=3072", VLM_F32, 1, 36928, 0, 36928, 3072, 1, false, 3, 1e-13);
 
   // exact Gram on the integer tensor cores
-  syrk_i8_case("i8x4 1 tile", 1, 64, 0, 64, 128, 0, true, 0, 1e-7);
-  syrk_i8_case("i8x4 d=768 ragged rows", 1, 1000, 0, 1000, 768, 0, true, 0, 1e-7);
-  syrk_i8_case("i8x4 d=384 positive", 1, 333, 0, 333, 384, 1, true, 0, 1e-7);
-  syrk_i8_case("i8x4 image slice", 4, 617, 40, 577, 768, 0, true, 0, 1e-7);
-  syrk_i8_case("i8x4 text d=3072", 1, 2560, 0, 2560, 3072, 1, false, 10, 1e-7);
-  syrk_i8_case("i8x4 image d=768", 1, 36928, 0, 36928, 768, 0, false, 10, 1e-7);
-  syrk_i8_case("i8x4 image d=3072", 1, 36928, 0, 36928, 3072, 1, false, 5, 1e-7);
+  syrk_i8_case<float>("i8x4 1 tile", VLM_F32, 1, 64, 0, 64, 128, 0, true, 0, 1e-7);
+  syrk_i8_case<float>("i8x4 d=768 ragged rows", VLM_F32, 1, 1000, 0, 1000, 768, 0, true, 0, 1e-7);
+  syrk_i8_case<float>("i8x4 d=384 positive", VLM_F32, 1, 333, 0, 333, 384, 1, true, 0, 1e-7);
+  syrk_i8_case<float>("i8x4 image slice", VLM_F32, 4, 617, 40, 577, 768, 0, true, 0, 1e-7);
+  syrk_i8_case<__half>("i8x4 f16 d=768", VLM_F16, 1, 1000, 0, 1000, 768, 0, true, 0, 1e-7);
+  syrk_i8_case<__nv_bfloat16>("i8x4 bf16 slice d=256", VLM_BF16, 3, 100, 20, 64, 256, 1, true, 0, 1e-7);
+  syrk_i8_case<float>("i8x4 text d=3072", VLM_F32, 1, 2560, 0, 2560, 3072, 1, false, 10, 1e-7);
+  syrk_i8_case<float>("i8x4 image d=768", VLM_F32, 1, 36928, 0, 36928, 768, 0, false, 10, 1e-7);
+  syrk_i8_case<float>("i8x4 image d=3072", VLM_F32, 1, 36928, 0, 36928, 3072, 1, false, 5, 1e-7);
 
   // split precision (3xTF32)
   syrk_split_case("tf32x3 1 tile", 1, 64, 0, 64, 128, 0, true, 0, 2e-6);

@@ -40,7 +40,7 @@ void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairS
                          int64_t seg_cap = 0);
 // exact Gram on the integer tensor cores (syrk_i8.cuh): fp32 activations -> four int8 digit planes -> fp64 Gram
 size_t syrk_i8x4_scratch_bytes(int64_t rows, int d);
-int syrk_i8x4_launch(const float* x, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride, void* scratch,
+int syrk_i8x4_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride, void* scratch,
                      double* g, int64_t ldg, cudaStream_t stream);
 
 // CTA-pair kernel (syrk_pair.cu + syrk_2sm.cuh: one tcgen05.mma.cta_group::2 stream per pair); needs whole 128-byte

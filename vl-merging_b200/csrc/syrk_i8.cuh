@@ -11,11 +11,12 @@
 // The dot products of digit planes are int8 x int8 -> int32 tensor-core products (tcgen05.mma kind::i8, exact: 2^12 per
 // product); the thirteen pairs with p + q <= 4 are kept.  (Group 4 matters: its D_2 . D_2 term is a sum of SQUARES on
 // the diagonal — with p + q <= 3 only, normally distributed activations came out 1.7e-7 off, on the B200 and in a numpy
-// emulation alike.  What is dropped now is below 1e-9 of sqrt(G_ii G_jj).)  Pairs of one group s = p + q share a scale, so a segment accumulates ONE group in one
-// int32 TMEM accumulator and its epilogue adds ldexp(acc, E_i + E_j - 10 - 7 s) to the fp64 Gram (red.global.add.f64,
-// coalesced through a per-warp shared-memory transpose: the split-K reduction, the sum over groups and the `+=`
-// across hook calls in one).  Quantisation error: 2^-27 of the
-// column maximum per element, unbiased.
+// emulation alike.  What is dropped now is below 1e-9 of sqrt(G_ii G_jj).)  Pairs of one group s = p + q share a
+// scale, so a segment accumulates one group per int32 TMEM accumulator, two groups at a time (below); its epilogue
+// merges the two exactly (acc1 * 128 + acc0 < 2^39), scales by 2^(E_i + E_j - 10 - 7 s) and adds the doubles to the
+// fp64 Gram with TMA reduce-adds (cp.reduce.async.bulk.tensor .add on an fp64 tensor map: the split-K reduction, the
+// sum over groups and the `+=` across hook calls in one).  Quantisation error: 2^-27 of the column maximum per
+// element, unbiased.
 //
 // Same CTA-pair structure as syrk_2sm_kernel (one tcgen05.mma.cta_group::2 stream, M = 256, N = 256; leader-owned
 // full / tempty barriers; six 32 KB stages, MN-major SWIZZLE_128B planes).  Every MMA consumes one 4 KB plane of A
@@ -26,8 +27,10 @@
 //   phase 2 (group 0): a stage = 128 rows of plane 0 ([A: 16 KB][B: 16 KB]), 4 MMAs per 32 KB (ingest-bound, 1/13 of
 //   the work);
 // one TMA box per operand per stage (three tensor maps over the same planes).  The accumulators belong to the
-// running segment, so its epilogue is not hidden (~10 % with 65536-row segments; int32 holds 2^17 rows of a
-// four-pair group).  (First version, one group per segment with 4 KB boxes: tensor pipe 43 % of elapsed in ncu.)
+// running segment, so its epilogue is not hidden; int32 holds 2^17 rows of a four-pair group, so segments are up to
+// 65536 rows long and epilogues are rare.  Measured (ncu, 36928 x 3072): IMMA pipe 91.8 % of elapsed, 1.33 ms.
+// History: one group per segment with 4 KB boxes: tensor pipe 43 %; per-element red.global.add.f64 epilogue (two per
+// element per phase, ldexp): 1.51 ms — the SM retires ~0.8 atomics per clock, 22 us per phase and CTA.
 #pragma once
 
 namespace vlm {
@@ -36,7 +39,7 @@ namespace {
 constexpr int kI8PlaneBytes = 32 * 128;   // 32 rows x 128 int8 columns
 constexpr int kI8Planes = 4;
 constexpr int kI8Phases = 3;              // {groups 4, 3}, {groups 2, 1}, {group 0}
-constexpr int kI8SlabBytes = 16384;         // 128 rows x 16 fp64 columns: one TMA reduce-add box, or the 4 transpose tiles
+constexpr int kI8SlabBytes = 16384;         // 128 rows x 16 fp64 columns: one TMA reduce-add box
 constexpr int kI8SmemBytes = k2Stages * k2StageBytes + kI8SlabBytes + 1280 + 1024;   // stages, slab, barriers
 
 struct I8Args {
@@ -81,9 +84,7 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, const v
 __device__ __forceinline__ double i8_pow2(int e) { return __hiloint2double((1023 + e) << 20, 0); }
 
 // segs: PairSeg with the phase (0: groups 4 and 3, 1: groups 2 and 1, 2: group 0) in bits 16.. of sb; k in 32-row chunks
-// TMA_EPI: the epilogue leaves through fp64 TMA reduce-adds (tm_g: G as a 2-D fp64 tensor, box 16 columns x 128 rows);
-// otherwise through per-element red.global.add.f64
-template <bool TMA_EPI>
+// tm_g: G as a 2-D fp64 tensor, box 16 columns x 128 rows (the epilogue's TMA reduce-adds)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 syrk_i8x4_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constant__ CUtensorMap tm_p1,
                  const __grid_constant__ CUtensorMap tm_p2, const __grid_constant__ CUtensorMap tm_g,
@@ -114,7 +115,7 @@ syrk_i8x4_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constan
     tma_prefetch_desc(&tm_p0);
     tma_prefetch_desc(&tm_p1);
     tma_prefetch_desc(&tm_p2);
-    if (TMA_EPI) tma_prefetch_desc(&tm_g);
+    tma_prefetch_desc(&tm_g);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kNS; ++i) {
@@ -223,7 +224,7 @@ syrk_i8x4_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constan
       acc_phase ^= 1;
     }
   } else if (warp >= 4) {
-    if constexpr (TMA_EPI) {
+    {
       // ===== epilogue (both CTAs): exact int32 sums of the phase's groups -> scaled fp64 -> TMA reduce-add into G =====
       // The two groups of a phase differ by 2^7 in scale: acc1 * 128 + acc0 is exact in 64-bit integers (< 2^39) and in
       // fp64, so a phase adds ONE double per element.  Scaling is by powers of two only (2^(E_row - 10 - 7 grp) and
@@ -284,62 +285,6 @@ syrk_i8x4_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constan
         acc_phase ^= 1;
       }
       if (epi_tid == 0) bulk_wait_group_read<0>();
-    } else {
-    // ===== epilogue (both CTAs): exact int32 sums of the phase's groups -> ONE scaled fp64 add per element =====
-    // The two groups of a phase differ by 2^7 in scale: acc1 * 128 + acc0 is exact in 64-bit integers (< 2^39) and in
-    // fp64, so a phase costs one red.global.add.f64 per element, not two.  Scaling is by powers of two only: the row
-    // thread multiplies by 2^(E_row - 10 - 7 grp), the column lane by 2^(E_col), both built from their exponent bits.
-    // A thread owns one accumulator ROW, so adding straight from its registers would touch 32 rows of G per warp
-    // instruction.  Each warp transposes 32 rows x 16 columns of doubles through shared memory; lane l then adds
-    // column (l & 15) of rows 2 i + (l >> 4): two contiguous 128-byte runs per instruction.
-    const int q = warp - 4;
-    double* tile = reinterpret_cast<double*>(slab) + q * (32 * 17);
-    uint32_t acc_phase = 0;
-    const uint32_t tempty0 = mapa_rank(smem_u32(tempty), 0);
-    const int lc = lane & 15, lr = lane >> 4;
-    for (int s = seg_begin; s < seg_end; ++s) {
-      const PairSeg seg = segs[s];
-      const int sb_t = seg.sb & 0xFFFF, ph = seg.sb >> 16;
-      const bool diag = seg.sa == sb_t;
-      const int n_off = (diag && rank == 1) ? 1 : 0;   // peer on a diagonal tile: only block (2a+1, 2a+1)
-      const int row_base = (2 * seg.sa + (int)rank) * 128 + q * 32;
-      const int col0 = (2 * sb_t + n_off) * 128;
-      const int grp = 4 - 2 * ph;                      // the group in accumulator 0 (the smaller scale of the phase)
-      const bool two = ph != 2;
-      mbar_wait(tfull, acc_phase);
-      tc_fence_after();
-      const double rscale = (row_base + lane < d) ? i8_pow2(__ldg(args.exps + row_base + lane) - 10 - 7 * grp) : 0.0;
-      const int nchunk = (row_base < d) ? min(4 * (2 - n_off), (d - col0 + 31) / 32) : 0;
-      for (int ch = 0; ch < nchunk; ++ch) {
-        uint32_t v[32], w[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + n_off * 128 + ch * 32;
-        tmem_ld_32x32b_x32(taddr, v);
-        if (two) tmem_ld_32x32b_x32(taddr + kAccCols, w);
-        tmem_ld_wait();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const long long c = two ? (long long)(int)w[16 * h + j] * 128 + (int)v[16 * h + j] : (long long)(int)v[16 * h + j];
-            tile[lane * 17 + j] = __ll2double_rn(c) * rscale;
-          }
-          __syncwarp();
-          const int c = col0 + ch * 32 + 16 * h + lc;
-          const double cscale = c < d ? i8_pow2(__ldg(args.exps + c)) : 0.0;
-          double* gp = args.g + (int64_t)(row_base + lr) * args.ldg + c;
-#pragma unroll 4
-          for (int i = 0; i < 16; ++i) {
-            const double val = tile[(2 * i + lr) * 17 + lc] * cscale;
-            if (row_base + 2 * i + lr < d && val != 0.0) atomicAdd(gp + (int64_t)(2 * i) * args.ldg, val);
-          }
-          __syncwarp();
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tempty0);
-      acc_phase ^= 1;
-    }
     }
   }
 
@@ -349,17 +294,32 @@ syrk_i8x4_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constan
 }
 
 // ---- pre-pass: column maxima -> exponents, then the four digit planes ---------------------------------------------
-__device__ __forceinline__ const float* i8_row_ptr(const float* x, int64_t r, int64_t ldx, int64_t seg_rows,
-                                                    int64_t seg_stride) {
+// X is fp32, or fp16 / bf16 (widened exactly: the reference calibrates under fp16 autocast, where the inputs of proj
+// and fc2 are half precision)
+template <typename T>
+__device__ __forceinline__ const T* i8_row_ptr(const T* x, int64_t r, int64_t ldx, int64_t seg_rows, int64_t seg_stride) {
   return seg_rows > 0 ? x + (r / seg_rows) * seg_stride + (r % seg_rows) * ldx : x + r * ldx;
+}
+// columns 4 q .. 4 q + 3 of a row
+__device__ __forceinline__ float4 i8_load4(const float* row, int q) { return __ldg(reinterpret_cast<const float4*>(row) + q); }
+__device__ __forceinline__ float4 i8_load4(const __half* row, int q) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(row) + q);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float4 i8_load4(const __nv_bfloat16* row, int q) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(row) + q);
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                     __uint_as_float(u.y & 0xffff0000u));
 }
 
 // grid (d / 128, row slabs); thread t of 32 x 8: columns 4 (t & 31) .. +3 of the block, rows (t >> 5) + 8 i of the slab;
 // four independent 16-byte loads in flight per thread (the pass is a pure HBM stream)
-__global__ void __launch_bounds__(256) i8_colmax_kernel(const float* __restrict__ x, int64_t rows, int d, int64_t ldx,
+template <typename T>
+__global__ void __launch_bounds__(256) i8_colmax_kernel(const T* __restrict__ x, int64_t rows, int d, int64_t ldx,
                                                         int64_t seg_rows, int64_t seg_stride, int64_t rows_per_slab,
                                                         unsigned* __restrict__ amax_bits) {
-  const int c = blockIdx.x * 128 + (threadIdx.x & 31) * 4;
+  const int cq = blockIdx.x * 32 + (threadIdx.x & 31);
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_slab, r1 = min(rows, r0 + rows_per_slab);
   float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
   int64_t r = r0 + (threadIdx.x >> 5);
@@ -367,13 +327,13 @@ __global__ void __launch_bounds__(256) i8_colmax_kernel(const float* __restrict_
     float4 v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      v[u] = __ldg(reinterpret_cast<const float4*>(i8_row_ptr(x, r + 8 * u, ldx, seg_rows, seg_stride) + c));
+      v[u] = i8_load4(i8_row_ptr(x, r + 8 * u, ldx, seg_rows, seg_stride), cq);
 #pragma unroll
     for (int u = 0; u < 4; ++u)
       m0 = fmaxf(m0, fabsf(v[u].x)), m1 = fmaxf(m1, fabsf(v[u].y)), m2 = fmaxf(m2, fabsf(v[u].z)), m3 = fmaxf(m3, fabsf(v[u].w));
   }
   for (; r < r1; r += 8) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(i8_row_ptr(x, r, ldx, seg_rows, seg_stride) + c));
+    const float4 v = i8_load4(i8_row_ptr(x, r, ldx, seg_rows, seg_stride), cq);
     m0 = fmaxf(m0, fabsf(v.x)), m1 = fmaxf(m1, fabsf(v.y)), m2 = fmaxf(m2, fabsf(v.z)), m3 = fmaxf(m3, fabsf(v.w));
   }
   // the block's 8 row groups are combined in shared memory first: one atomic per column per block (with one per
@@ -423,20 +383,21 @@ __device__ __forceinline__ void i8_slice_store(const float4& v, const float4& sc
 }
 // block b: rows b, b + gridDim.x, ... (four rows per trip); thread t: column quads t, t + 256, ... of each row — no
 // index division, 4 x 16 bytes in flight per thread
-__global__ void __launch_bounds__(256, 4) i8_slice_kernel(const float* __restrict__ x, int64_t rows, int d, int64_t ldx,
+template <typename T>
+__global__ void __launch_bounds__(256, 4) i8_slice_kernel(const T* __restrict__ x, int64_t rows, int d, int64_t ldx,
                                                        int64_t seg_rows, int64_t seg_stride,
                                                        const float* __restrict__ scales, int8_t* __restrict__ planes) {
   const int d4 = d >> 2;
   const int64_t plane = rows * (int64_t)d;
   const int64_t G = gridDim.x;
   for (int64_t r0 = blockIdx.x; r0 < rows; r0 += 4 * G) {
-    const float* src[4];
+    const T* src[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) src[u] = i8_row_ptr(x, min(r0 + u * G, rows - 1), ldx, seg_rows, seg_stride);
     for (int cq = threadIdx.x; cq < d4; cq += 256) {
       float4 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(src[u]) + cq);
+      for (int u = 0; u < 4; ++u) v[u] = i8_load4(src[u], cq);
       const float4 e = __ldg(reinterpret_cast<const float4*>(scales) + cq);
 #pragma unroll
       for (int u = 0; u < 4; ++u)

@@ -404,8 +404,83 @@ int tf32_split_launch(const float* x, int64_t rows, int d, int64_t ldx, int64_t 
 // [column maxima: d uints], 16-byte aligned.
 size_t syrk_i8x4_scratch_bytes(int64_t rows, int d) { return (size_t)4 * rows * d + (size_t)8 * d + 64; }
 
-int syrk_i8x4_launch(const float* x, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride, void* scratch,
-                     double* g, int64_t ldg, cudaStream_t stream) {
+// The int8 schedule: every (tile, K range) of the floating-point schedule runs once per phase.  When there are fewer
+// (tile, phase) pairs than clusters (768-wide Grams: 6 tiles), the clusters of a tile are divided among its phases
+// instead — each cluster then runs ONE segment of ONE phase and pays one pipeline fill and one exposed epilogue, not
+// three (ncu, 36928 x 768: IMMA pipe 64 % of elapsed with three).  Phase weights = tensor time per 32 rows in units
+// of one MMA (phase 2 is ingest-bound: a little over one).
+static void build_i8_schedule(int64_t kc, int d, int C, std::vector<PairSeg>* segs, std::vector<int>* off) {
+  const int nsb = (d + 255) / 256;
+  const int T = nsb * (nsb + 1) / 2;
+  segs->clear();
+  off->assign(1, 0);
+  static const bool split_on = [] {
+    const char* e = getenv("VLM_I8_PHASE_SPLIT");
+    return e ? atoi(e) != 0 : true;
+  }();
+  const int m = C / T;                       // clusters per tile
+  if (split_on && m >= 3 && kc >= 64) {
+    const double w[3] = {7.0, 5.0, 1.15};
+    const double fixed = 200.0;              // pipeline fill + exposed epilogue of one segment, in 32-row MMA units
+    int best[3] = {0, 0, 0};
+    double best_t = 1e30;
+    for (int n0 = 1; n0 <= m - 2; ++n0)
+      for (int n1 = 1; n0 + n1 <= m - 1; ++n1) {
+        const int n2 = m - n0 - n1;
+        const double t = std::max(w[0] / n0, std::max(w[1] / n1, w[2] / n2));
+        if (t < best_t - 1e-12) best_t = t, best[0] = n0, best[1] = n1, best[2] = n2;
+      }
+    const double t_split = best_t * (double)kc + fixed;
+    const double t_all = (w[0] + w[1] + w[2]) / m * (double)kc + 3 * fixed;
+    if (t_split < t_all) {
+      for (int a = 0; a < nsb; ++a)
+        for (int b = a; b < nsb; ++b)
+          for (int ph = 0; ph < kI8Phases; ++ph)
+            for (int i = 0; i < best[ph]; ++i) {
+              // phase 2 consumes 128-row stages: cut its K range on multiples of 4 chunks
+              const int64_t g = ph == 2 ? 4 : 1, units = (kc + g - 1) / g;
+              const int64_t k0 = std::min(kc, units * i / best[ph] * g), k1 = std::min(kc, units * (i + 1) / best[ph] * g);
+              if (k1 > k0) {
+                // int32 accumulation is exact for 2^17 rows; 2048 chunks = 65536 rows per segment
+                for (int64_t k = k0; k < k1; k += 2048)
+                  segs->push_back({a, b | (ph << 16), (int)k, (int)std::min(k1, k + 2048)});
+                off->push_back((int)segs->size());
+              }
+            }
+      return;
+    }
+  }
+  std::vector<PairSeg> base;
+  std::vector<int> boff;
+  // int32 accumulation of a four-pair group is exact for 2^17 rows (|digit| <= 64); 2048 chunks = 65536 rows per
+  // segment keeps the (exposed) epilogues rare
+  build_pair_schedule(kc, d, C, &base, &boff, 2048);
+  for (size_t c = 0; c + 1 < boff.size(); ++c) {
+    for (int i = boff[c]; i < boff[c + 1]; ++i)
+      for (int ph = 0; ph < kI8Phases; ++ph) segs->push_back({base[i].sa, base[i].sb | (ph << 16), base[i].k0, base[i].k1});
+    off->push_back((int)segs->size());
+  }
+}
+
+template <typename T>
+static int i8_prepass(const T* x, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride, unsigned* amax,
+                      int* exps, int8_t* planes, int nsm, cudaStream_t stream) {
+  // column maxima -> exponents (+ the float scales, written over the maxima) -> digit planes
+  VLM_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned) * d, stream));
+  const int64_t slabs = std::max<int64_t>(1, std::min<int64_t>((rows + 255) / 256, (int64_t)nsm * 16 / std::max(1, d / 128)));
+  const int64_t rps = (rows + slabs - 1) / slabs;
+  i8_colmax_kernel<T><<<dim3((unsigned)(d / 128), (unsigned)((rows + rps - 1) / rps)), 256, 0, stream>>>(
+      x, rows, d, ldx, seg_rows, seg_stride, rps, amax);
+  i8_exps_kernel<<<(d + 255) / 256, 256, 0, stream>>>(amax, d, exps);
+  i8_slice_kernel<T><<<(unsigned)std::max<int64_t>(1, std::min<int64_t>(rows, (int64_t)nsm * 4)), 256, 0, stream>>>(
+      x, rows, d, ldx, seg_rows, seg_stride, reinterpret_cast<const float*>(amax), planes);
+  VLM_CUDA(cudaGetLastError());
+  count_launch(3);
+  return 0;
+}
+
+int syrk_i8x4_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride,
+                     void* scratch, double* g, int64_t ldg, cudaStream_t stream) {
   int dev = 0, nsm = 0;
   VLM_CUDA(cudaGetDevice(&dev));
   if (int rc = device_sm_count(&nsm)) return rc;
@@ -414,17 +489,14 @@ int syrk_i8x4_launch(const float* x, int64_t rows, int d, int64_t ldx, int64_t s
   int8_t* planes = static_cast<int8_t*>(scratch);
   int* exps = reinterpret_cast<int*>(planes + (((size_t)4 * rows * d + 15) & ~(size_t)15));
   unsigned* amax = reinterpret_cast<unsigned*>(exps + d);
-  // pre-pass: column maxima -> exponents -> digit planes
-  VLM_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned) * d, stream));
-  const int64_t slabs = std::max<int64_t>(1, std::min<int64_t>((rows + 255) / 256, (int64_t)nsm * 16 / std::max(1, d / 128)));
-  const int64_t rps = (rows + slabs - 1) / slabs;
-  i8_colmax_kernel<<<dim3((unsigned)(d / 128), (unsigned)((rows + rps - 1) / rps)), 256, 0, stream>>>(
-      x, rows, d, ldx, seg_rows, seg_stride, rps, amax);
-  i8_exps_kernel<<<(d + 255) / 256, 256, 0, stream>>>(amax, d, exps);
-  i8_slice_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>(rows, (int64_t)nsm * 4)), 256, 0, stream>>>(
-      x, rows, d, ldx, seg_rows, seg_stride, reinterpret_cast<const float*>(amax), planes);
-  VLM_CUDA(cudaGetLastError());
-  count_launch(3);
+  int rc;
+  if (dtype == VLM_F32)
+    rc = i8_prepass(static_cast<const float*>(x), rows, d, ldx, seg_rows, seg_stride, amax, exps, planes, nsm, stream);
+  else if (dtype == VLM_F16)
+    rc = i8_prepass(static_cast<const __half*>(x), rows, d, ldx, seg_rows, seg_stride, amax, exps, planes, nsm, stream);
+  else
+    rc = i8_prepass(static_cast<const __nv_bfloat16*>(x), rows, d, ldx, seg_rows, seg_stride, amax, exps, planes, nsm, stream);
+  if (rc) return rc;
 
   // three views of the planes: 32 rows of all four (groups 4, 3), 32 rows of planes 0..2 (groups 2, 1), 128 rows of
   // plane 0 (group 0)
@@ -454,19 +526,12 @@ int syrk_i8x4_launch(const float* x, int64_t rows, int d, int64_t ldx, int64_t s
   const int64_t kc = (rows + 31) / 32;
   VLM_REQUIRE(kc < (int64_t)1 << 30, VLM_ERR_INVALID_ARG, "vlm_syrk_accum_i8x4: too many row chunks");
   std::lock_guard<std::mutex> lk(g_mu2);
-  auto key = std::make_tuple(dev, kc, d, -8, nsm);   // bk = -8: the int8 schedule (every segment once per phase)
+  auto key = std::make_tuple(dev, kc, d, -8, nsm);   // bk = -8: the int8 schedule
   auto it = g_sched2.find(key);
   if (it == g_sched2.end()) {
-    std::vector<PairSeg> base, segs;
-    std::vector<int> boff, off(1, 0);
-    // int32 accumulation of a four-pair group is exact for 2^17 rows (|digit| <= 64); 2048 chunks = 65536 rows per
-    // segment keeps the epilogues (64K fp64 adds per CTA) rare
-    build_pair_schedule(kc, d, nsm / 2, &base, &boff, 2048);
-    for (size_t c = 0; c + 1 < boff.size(); ++c) {
-      for (int i = boff[c]; i < boff[c + 1]; ++i)
-        for (int ph = 0; ph < kI8Phases; ++ph) segs.push_back({base[i].sa, base[i].sb | (ph << 16), base[i].k0, base[i].k1});
-      off.push_back((int)segs.size());
-    }
+    std::vector<PairSeg> segs;
+    std::vector<int> off;
+    build_i8_schedule(kc, d, nsm / 2, &segs, &off);
     DeviceSchedule2 ds;
     ds.nclusters = (int)off.size() - 1;
     VLM_CUDA(cudaMalloc(&ds.d_segs, std::max<size_t>(1, segs.size()) * sizeof(PairSeg)));
@@ -478,14 +543,10 @@ int syrk_i8x4_launch(const float* x, int64_t rows, int d, int64_t ldx, int64_t s
   }
   const DeviceSchedule2& sched = it->second;
   const int smem = kI8SmemBytes;
-  static const bool tma_epi = [] {
-    const char* e = getenv("VLM_I8_TMA_EPILOGUE");
-    return e ? atoi(e) != 0 : true;
-  }();
-  auto kernel = tma_epi ? syrk_i8x4_kernel<true> : syrk_i8x4_kernel<false>;
-  VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  VLM_CUDA(cudaFuncSetAttribute(syrk_i8x4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   I8Args args{g, ldg, exps};
-  kernel<<<2 * sched.nclusters, kThreads, smem, stream>>>(tm_p[0], tm_p[1], tm_p[2], tm_g, sched.d_segs, sched.d_off, d, args);
+  syrk_i8x4_kernel<<<2 * sched.nclusters, kThreads, smem, stream>>>(tm_p[0], tm_p[1], tm_p[2], tm_g, sched.d_segs, sched.d_off,
+                                                                    d, args);
   VLM_CUDA(cudaGetLastError());
   count_launch();
   return 0;

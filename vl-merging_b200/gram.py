@@ -126,10 +126,10 @@ class GramCache:
         "fp64": the reference's own arithmetic — fp64 products, fp64 accumulation, fp64 Gram buffers
         (vlm_syrk_accum_f64, DMMA tensor cores); the mode that carries regmean to its 1e-4 tolerance.  Launches
         immediately (no grouping).
-        "int8x4": the same RegMean-grade fp64 Grams from the INTEGER tensor cores — every fp32 column is scaled by a
+        "int8x4": the same RegMean-grade fp64 Grams from the INTEGER tensor cores — every column is scaled by a
         power of two and cut into four int8 digit planes, whose products accumulate exactly in int32
-        (vlm_syrk_accum_i8x4; Gram error ~1e-8, regmean within 1e-4 like "fp64") at about a third of the cost; small
-        problems, 16-bit activations and widths that are not multiples of 128 take the fp64 path.
+        (vlm_syrk_accum_i8x4; Gram error ~1e-9, regmean within 1e-4 like "fp64") at an eighth of the cost (fp32, fp16
+        and bf16 activations alike); small problems and widths that are not multiples of 128 take the fp64 path.
         defer_bytes > 0: an activation of at most that many bytes is not launched on its own (the Gram of a
         40-token text batch is launch-bound: ~7 us of fixed cost for ~2 us of tensor-core work, and a 768-wide
         image Gram exposes its prologue and final epilogue); the hook keeps a REFERENCE to it (no copy) and
@@ -223,12 +223,12 @@ class GramCache:
         self._finalized = False
         code = _DTYPES[keep.dtype]
         nbytes = rows * ldx * elem
-        if self.precision == "int8x4" and code == _lib.VLM_F32 and d % 128 == 0 and rows * d >= (1 << 22) \
+        if self.precision == "int8x4" and d % 128 == 0 and rows * d >= (1 << 21) \
                 and ptr % 16 == 0 and ldx % 4 == 0 and seg_stride % 4 == 0:
             nbytes = int(self._lib.vlm_syrk_i8x4_scratch_bytes(rows, d))
             scratch = self._plane_scratch((nbytes + 3) // 4)
-            _lib.check(self._lib.vlm_syrk_accum_i8x4(ptr, rows, d, ldx, seg_rows, seg_stride, scratch.data_ptr(), nbytes,
-                                                     g.data_ptr(), g.stride(0), self._launch_stream(keep)))
+            _lib.check(self._lib.vlm_syrk_accum_i8x4(ptr, code, rows, d, ldx, seg_rows, seg_stride, scratch.data_ptr(),
+                                                     nbytes, g.data_ptr(), g.stride(0), self._launch_stream(keep)))
             return
         if self.dtype == torch.float64:
             _lib.check(self._lib.vlm_syrk_accum_f64(ptr, code, rows, d, ldx, seg_rows, seg_stride,
