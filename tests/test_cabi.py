@@ -43,6 +43,15 @@ def test_argument_validation_happens_before_any_cuda_call():
     assert L.vlm_sym_finalize(None, 128, 128, None, 0, None) == -1
     assert L.vlm_merge_plan_run(None, None) == -1
     assert L.vlm_regmean_rhs(None, 1, 1, 1, None, 3, 1, 1.0, None, 1, 0, None) == -1
+    # the integer-tensor-core Gram: dtype, width and alignment are checked up front
+    buf = (ctypes.c_char * 4096)()
+    a16 = (ctypes.addressof(buf) + 15) & ~15
+    assert L.vlm_syrk_accum_i8x4(a16, 9, 32, 128, 128, 0, 0, a16, 1 << 20, a16, 128, None) == -1        # bad dtype
+    assert L.vlm_syrk_accum_i8x4(a16, vlm._lib.VLM_F32, 32, 96, 96, 0, 0, a16, 1 << 20, a16, 96, None) != 0   # d % 128
+    assert b"multiple of 128" in L.vlm_last_error()
+    assert L.vlm_syrk_accum_i8x4(a16 + 4, vlm._lib.VLM_F16, 32, 128, 128, 0, 0, a16, 1 << 20, a16, 128, None) != 0  # x alignment
+    assert L.vlm_syrk_accum_i8x4(a16, vlm._lib.VLM_F32, 32, 128, 128, 0, 0, a16, 16, a16, 128, None) == -1  # scratch too small
+    assert L.vlm_syrk_i8x4_scratch_bytes(32, 128) >= 4 * 32 * 128 + 8 * 128
     seg = vlm._lib.MergeSeg()
     seg.n_src = 9
     plan = ctypes.c_void_p()
