@@ -141,6 +141,9 @@ int vlm_sym_pack_upper(const float* g, int d, int64_t ldg, float* packed, void* 
 /* Inverse: the full symmetric d x d matrix, as fp32 (out_dtype VLM_F32) or widened to fp64 (VLM_F64, the
  * reference's Gram dtype). */
 int vlm_sym_unpack(const float* packed, int d, void* out, int out_dtype, int64_t ldo, void* stream);
+/* The same for fp64 Grams (the int8x4 / fp64 cache modes): packed fp64 upper triangle <-> full symmetric fp64. */
+int vlm_sym_pack_upper_f64(const double* g, int d, int64_t ldg, double* packed, void* stream);
+int vlm_sym_unpack_f64(const double* packed, int d, double* out, int64_t ldo, void* stream);
 
 /* Host-only view of vlm_syrk_accum's work decomposition for (rows, d) on a device with nsm SMs
  * (elem_bytes 4 = f32, 2 = bf16/f16): writes segments as 5 int32 each {row_block_col0, col_block_col0,

@@ -30,10 +30,14 @@ def _worker(rank, world, port, ret):
         model = vlm.init_synthetic_(vlm.VLMo(cfg).eval(), seed=1).cuda()
         cache = vlm.GramCache()
         cache.register(model)
+        cache8 = vlm.GramCache(precision="int8x4")       # fp64 Gram buffers: the packed fp64 exchange
+        cache8.register(model)
         with torch.no_grad():
             model(vlm.synthetic_batch(2, cfg, seed=50 + rank, device="cuda"))   # this rank's shard of the calibration set
         cache.all_reduce()
+        cache8.all_reduce()
         grams = cache.state_dict()
+        grams8 = cache8.state_dict()
         sd = {k: v.detach() for k, v in model.state_dict().items()}
         mcfg = dict(vlffn_start_layer_index=10, only_activate_used_experts=False, merge_ratio=0.5, sum_lambda=0.75,
                     scaling_for_non_diag=0.9, loss_names={"irtr": 1.0, "vqa": 0, "nlvr2": 0})
@@ -49,6 +53,8 @@ def _worker(rank, world, port, ret):
         pick = ["transformer.blocks.0.attn.qkv.weight", "transformer.blocks.11.mlp.fc2.weight", "transformer.blocks.4.norm2.bias"]
         ret[rank] = {
             "grams": {k: grams[k].numpy() for k in ("transformer.blocks.0.attn.v", "transformer.blocks.7.mlp.l.fc2")},
+            "grams8": {k: grams8[k].numpy() for k in ("transformer.blocks.0.attn.v", "transformer.blocks.7.mlp.l.fc2")},
+            "reduce_bytes": (cache.last_reduce_bytes, cache8.last_reduce_bytes),
             "n_grams": len(grams),
             "merged": {k: merged[k].cpu().numpy() for k in pick},
             "regmean": {k: rm[k].cpu().numpy() for k in pick},
@@ -75,13 +81,19 @@ def test_two_rank_calibration_and_sharded_merge():
     model = vlm.init_synthetic_(vlm.VLMo(cfg).eval(), seed=1).cuda()
     cache = vlm.GramCache()
     cache.register(model)
+    cache8 = vlm.GramCache(precision="int8x4")
+    cache8.register(model)
     with torch.no_grad():
         for rank in range(2):
             model(vlm.synthetic_batch(2, cfg, seed=50 + rank, device="cuda"))
-    want = cache.state_dict()
+    want, want8 = cache.state_dict(), cache8.state_dict()
     for k, g in r0["grams"].items():
         assert np.array_equal(g, r1["grams"][k])
         assert np.linalg.norm(g - want[k].numpy()) <= 1e-5 * np.linalg.norm(want[k].numpy())
+    for k, g in r0["grams8"].items():                       # the RegMean-grade cache: packed fp64 upper triangles travel
+        assert np.array_equal(g, r1["grams8"][k]) and np.array_equal(g, g.T)
+        assert np.linalg.norm(g - want8[k].numpy()) <= 1e-13 * np.linalg.norm(want8[k].numpy())
+    assert r0["reduce_bytes"][1] == 2 * r0["reduce_bytes"][0] == 2 * 4 * sum(d * (d + 1) // 2 for d in [192] * 72 + [768] * 24)
     sd = {k: v.detach() for k, v in model.state_dict().items()}
     mcfg = dict(vlffn_start_layer_index=10, only_activate_used_experts=False, merge_ratio=0.5, sum_lambda=0.75,
                 scaling_for_non_diag=0.9, loss_names={"irtr": 1.0, "vqa": 0, "nlvr2": 0})

@@ -70,6 +70,8 @@ SIGNATURES = {
     "vlm_sym_finalize": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p]),
     "vlm_sym_pack_upper": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "vlm_sym_unpack": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p]),
+    "vlm_sym_pack_upper_f64": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "vlm_sym_unpack_f64": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p]),
     "vlm_syrk_schedule_host": (c_int, [c_int64, c_int, c_int, c_int, POINTER(c_int32), c_int, POINTER(c_int32),
                                        c_int, POINTER(c_int)]),
     "vlm_syrk_pair_schedule_host": (c_int, [c_int64, c_int, c_int, c_int, POINTER(c_int32), c_int, POINTER(c_int32),

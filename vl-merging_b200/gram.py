@@ -364,14 +364,15 @@ class GramCache:
     def all_reduce(self, group=None, packed=True):
         """Data-parallel calibration: sum the per-rank Gram buffers (ONE NCCL all-reduce over NVLink).
         The reference has no such step (every DDP rank writes its own file).
-        packed (fp32 caches): only the upper triangles of the Grams that fired travel — vlm_sym_pack_upper into one
-        flat buffer, one all-reduce of it (VLMo-base: 0.54 GB instead of the 1.17 GB arena with its lower triangles
-        and never-fired `vl` experts), vlm_sym_unpack back into the full symmetric buffers (which leaves the cache
-        finalized).  packed=False, or an fp64 cache: one all-reduce of the whole arena."""
+        packed: only the upper triangles of the Grams that fired travel — vlm_sym_pack_upper(_f64) into one flat
+        buffer, one all-reduce of it (VLMo-base: 0.54 GB instead of the 1.17 GB arena with its lower triangles
+        and never-fired `vl` experts; twice that for the fp64 Grams of the int8x4 / fp64 modes), vlm_sym_unpack(_f64)
+        back into the full symmetric buffers (which leaves the cache finalized).  packed=False: one all-reduce of the
+        whole arena."""
         import torch.distributed as dist
 
         self.flush()
-        if not packed or self.dtype != torch.float32:
+        if not packed:
             return reduce_gram_buffers(self.buffers, self._arenas, self.calls, self.rows, group)
         names = agree_on_buffers(self.buffers, group,
                                  lambda d: torch.zeros(d, d, dtype=self.dtype, device=self.device))
@@ -379,23 +380,29 @@ class GramCache:
         live = [n for n in names if self.calls[n] > 0]
         if not live:
             return
+        f64 = self.dtype == torch.float64
+        esz = 8 if f64 else 4
         sizes = [self.buffers[n].shape[0] * (self.buffers[n].shape[0] + 1) // 2 for n in live]
-        flat = torch.empty(sum(sizes), dtype=torch.float32, device=self.device)
+        flat = torch.empty(sum(sizes), dtype=self.dtype, device=self.device)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         off = 0
         for n, sz in zip(live, sizes):
             g = self.buffers[n]
-            _lib.check(self._lib.vlm_sym_pack_upper(g.data_ptr(), g.shape[0], g.stride(0), flat.data_ptr() + 4 * off, stream))
+            pack = self._lib.vlm_sym_pack_upper_f64 if f64 else self._lib.vlm_sym_pack_upper
+            _lib.check(pack(g.data_ptr(), g.shape[0], g.stride(0), flat.data_ptr() + esz * off, stream))
             off += sz
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         off = 0
         for n, sz in zip(live, sizes):
             g = self.buffers[n]
-            _lib.check(self._lib.vlm_sym_unpack(flat.data_ptr() + 4 * off, g.shape[0], g.data_ptr(), _lib.VLM_F32,
-                                                g.stride(0), stream))
+            if f64:
+                _lib.check(self._lib.vlm_sym_unpack_f64(flat.data_ptr() + esz * off, g.shape[0], g.data_ptr(), g.stride(0), stream))
+            else:
+                _lib.check(self._lib.vlm_sym_unpack(flat.data_ptr() + esz * off, g.shape[0], g.data_ptr(), _lib.VLM_F32,
+                                                    g.stride(0), stream))
             off += sz
         self._finalized = True
-        self.last_reduce_bytes = flat.numel() * 4
+        self.last_reduce_bytes = flat.numel() * esz
 
     def finalize(self):
         """Mirror the upper triangles into the lower ones (after the last accumulate / all_reduce)."""
