@@ -153,7 +153,9 @@ int vlm_syrk_schedule_host(int64_t rows, int d, int elem_bytes, int nsm, int32_t
                            int32_t* off_out, int off_cap, int* ncta_out);
 
 /* Same for the CTA-pair kernel (the default when d is a whole number of 128-byte column groups): 4 int32 per
- * segment {super_row, super_col (256-column units), chunk_begin, chunk_end} and ncluster+1 offsets. */
+ * segment {super_row, super_col (256-column units), chunk_begin, chunk_end} and ncluster+1 offsets.
+ * elem_bytes 1 = the int8 digit-plane kernel (vlm_syrk_accum_i8x4): 32-row chunks, the phase (0, 1, 2) in bits 16.. of
+ * super_col. */
 int vlm_syrk_pair_schedule_host(int64_t rows, int d, int elem_bytes, int nsm, int32_t* segs_out, int cap,
                                 int32_t* off_out, int off_cap, int* ncluster_out);
 

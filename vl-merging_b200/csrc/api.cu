@@ -245,12 +245,15 @@ extern "C" int vlm_syrk_schedule_host(int64_t rows, int d, int elem_bytes, int n
 
 extern "C" int vlm_syrk_pair_schedule_host(int64_t rows, int d, int elem_bytes, int nsm, int32_t* segs_out, int cap,
                                            int32_t* off_out, int off_cap, int* ncluster_out) {
-  VLM_REQUIRE(rows > 0 && d > 0 && (elem_bytes == 2 || elem_bytes == 4) && nsm > 1 && ncluster_out, VLM_ERR_INVALID_ARG,
-              "vlm_syrk_pair_schedule_host: bad arguments");
+  VLM_REQUIRE(rows > 0 && d > 0 && (elem_bytes == 1 || elem_bytes == 2 || elem_bytes == 4) && nsm > 1 && ncluster_out,
+              VLM_ERR_INVALID_ARG, "vlm_syrk_pair_schedule_host: bad arguments");
   const int bk = 128 / elem_bytes;
   std::vector<int32_t> flat;
   std::vector<int> off;
-  build_syrk_pair_schedule_host((rows + bk - 1) / bk, d, nsm, &flat, &off);
+  if (elem_bytes == 1)
+    build_syrk_i8_schedule_host((rows + 31) / 32, d, nsm, &flat, &off);
+  else
+    build_syrk_pair_schedule_host((rows + bk - 1) / bk, d, nsm, &flat, &off);
   *ncluster_out = (int)off.size() - 1;
   VLM_REQUIRE((int)flat.size() <= 4 * cap && (int)off.size() <= off_cap, VLM_ERR_INVALID_ARG,
               "vlm_syrk_pair_schedule_host: output capacity too small (%d segments)", (int)flat.size() / 4);

@@ -43,6 +43,8 @@ size_t syrk_i8x4_scratch_bytes(int64_t rows, int d);
 int syrk_i8x4_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride, void* scratch,
                      double* g, int64_t ldg, cudaStream_t stream);
 
+void build_syrk_i8_schedule_host(int64_t kc, int d, int nsm, std::vector<int32_t>* flat, std::vector<int>* off);
+
 // CTA-pair kernel (syrk_pair.cu + syrk_2sm.cuh: one tcgen05.mma.cta_group::2 stream per pair); needs whole 128-byte
 // column groups
 bool syrk_pair_supported(int dtype, int d, int64_t ldx);

@@ -318,6 +318,20 @@ void build_syrk_pair_schedule_host(int64_t kc, int d, int nsm, std::vector<int32
   }
 }
 
+// Host view of the int8 schedule (kc in 32-row chunks): {super_row, super_col | phase << 16, k0, k1} per cluster.
+static void build_i8_schedule(int64_t kc, int d, int C, std::vector<PairSeg>* segs, std::vector<int>* off);
+void build_syrk_i8_schedule_host(int64_t kc, int d, int nsm, std::vector<int32_t>* flat, std::vector<int>* off) {
+  std::vector<PairSeg> segs;
+  build_i8_schedule(kc, d, nsm / 2, &segs, off);
+  flat->clear();
+  for (const PairSeg& s : segs) {
+    flat->push_back(s.sa);
+    flat->push_back(s.sb);
+    flat->push_back(s.k0);
+    flat->push_back(s.k1);
+  }
+}
+
 bool syrk_pair_supported(int dtype, int d, int64_t ldx) {
   return d % (128 / elem_bytes(dtype)) == 0 && ldx >= d;  // whole 128-byte column groups (the 3-D tensor map needs them)
 }
@@ -407,19 +421,16 @@ size_t syrk_i8x4_scratch_bytes(int64_t rows, int d) { return (size_t)4 * rows * 
 // The int8 schedule: every (tile, K range) of the floating-point schedule runs once per phase.  When there are fewer
 // (tile, phase) pairs than clusters (768-wide Grams: 6 tiles), the clusters of a tile are divided among its phases
 // instead — each cluster then runs ONE segment of ONE phase and pays one pipeline fill and one exposed epilogue, not
-// three (ncu, 36928 x 768: IMMA pipe 64 % of elapsed with three).  Phase weights = tensor time per 32 rows in units
+// three (ncu, 36928 x 768: IMMA pipe 64 % of elapsed with three; A/B on the B200, profiles/r02_syrk_i8x4_cases.log:
+// 2560 x 768 0.063 -> 0.043 ms, 9216 x 768 0.086 -> 0.069, 36928 x 768 0.209 -> 0.196).  Phase weights = tensor time per 32 rows in units
 // of one MMA (phase 2 is ingest-bound: a little over one).
 static void build_i8_schedule(int64_t kc, int d, int C, std::vector<PairSeg>* segs, std::vector<int>* off) {
   const int nsb = (d + 255) / 256;
   const int T = nsb * (nsb + 1) / 2;
   segs->clear();
   off->assign(1, 0);
-  static const bool split_on = [] {
-    const char* e = getenv("VLM_I8_PHASE_SPLIT");
-    return e ? atoi(e) != 0 : true;
-  }();
   const int m = C / T;                       // clusters per tile
-  if (split_on && m >= 3 && kc >= 64) {
+  if (m >= 3 && kc >= 64) {
     const double w[3] = {7.0, 5.0, 1.15};
     const double fixed = 200.0;              // pipeline fill + exposed epilogue of one segment, in 32-row MMA units
     int best[3] = {0, 0, 0};
