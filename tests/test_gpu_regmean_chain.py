@@ -147,3 +147,18 @@ def test_tensor_core_gram_modes_are_reported(chain, alpha):
         assert max(e.values()) < 0.2, (m, e)
     fc2 = [k for k in errs["tf32"] if ".fc2." in k]
     assert all(errs["tf32x3"][k] <= 1e-4 for k in fc2), errs["tf32x3"]
+
+
+def test_regmean_warns_about_tf32_grams_without_regularisation(chain):
+    """scaling_for_non_diag = 1 on single-pass TF32 Grams is the combination that misses 1e-4: regmean says so and
+    names the RegMean-grade modes; it stays quiet for those modes and for scaling < 1."""
+    import warnings
+
+    cfg, sd, np_sd, caches, ref, np_ref = chain
+    mcfg = dict(vlffn_start_layer_index=2, loss_names={"irtr": 1.0, "vqa": 0, "nlvr2": 0}, scaling_for_non_diag=1.0)
+    with pytest.warns(RuntimeWarning, match="int8x4"):
+        vlm.regmean(sd, mcfg, gram_matrices=caches["tf32"], num_layers=2)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        vlm.regmean(sd, mcfg, gram_matrices=caches["int8x4"], num_layers=2)
+        vlm.regmean(sd, {**mcfg, "scaling_for_non_diag": 0.9}, gram_matrices=caches["tf32"], num_layers=2)

@@ -485,8 +485,16 @@ def regmean(state_dict, config, device=None, num_layers=12, group=None, stats=No
         gpath = config["gram_matrices"]
         # the packed fp32 container of gramfile.py, or the reference's own pickle of fp64 matrices
         gram_matrices = gramfile.load_packed(gpath, device) if gramfile.is_packed_file(gpath) else _load(gpath)
-    grams = _as_gram_dict(gram_matrices)
     alpha = float(config["scaling_for_non_diag"])
+    if alpha == 1.0 and getattr(gram_matrices, "precision", None) in ("tf32", "tf32x3"):
+        import warnings
+
+        # measured on the B200: LayerNorm-fed linears come out 1e-2 off with single-pass TF32 Grams
+        warnings.warn(f"regmean with scaling_for_non_diag = 1 on Grams cached with precision={gram_matrices.precision!r}: "
+                      "the inverse of an unregularised Gram sum amplifies the tensor core's fp32 accumulation error; "
+                      "calibrate with GramCache(precision='int8x4') (or 'fp64') for the reference's 1e-4",
+                      RuntimeWarning, stacklevel=2)
+    grams = _as_gram_dict(gram_matrices)
     ops = plan_regmean(state_dict.keys(), grams.keys(), config, num_layers)
     todo = [op for op in ops if not op.passthrough]
     mean_ops = [op for op in todo if op.regmean is None]
