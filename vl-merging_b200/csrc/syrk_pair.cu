@@ -429,7 +429,7 @@ static void build_i8_schedule(int64_t kc, int d, int C, std::vector<PairSeg>* se
   const int T = nsb * (nsb + 1) / 2;
   segs->clear();
   off->assign(1, 0);
-  const int m = C / T;                       // clusters per tile
+  const int m = (int)std::min<int64_t>(C / T, kc / 6);    // clusters per tile; no K piece much below 8 chunks (measured: 2560 x 768 is fastest with all 12)
   if (m >= 3 && kc >= 64) {
     const double w[3] = {7.0, 5.0, 1.15};
     const double fixed = 200.0;              // pipeline fill + exposed epilogue of one segment, in 32-row MMA units
