@@ -208,6 +208,14 @@ int vlm_gram_scale_accum(const void* g, int g_dtype, int d, int64_t ldg, double 
 int vlm_regmean_rhs(const float* w, int out_f, int in_f, int64_t ldw,
                     const void* g, int g_dtype, int64_t ldg, double alpha,
                     double* acc, int64_t ldacc, int accumulate, void* stream);
+/* The same with the left operand W - W_base (same shape and pitch; the difference is formed in fp64).  With M experts
+ * and S = sum Ghat_m:  (sum_m W_m Ghat_m) S^-1  =  W_base + (sum_{m != base} (W_m - W_base) Ghat_m) S^-1,  one GEMM
+ * fewer than the reference's formula (half the flops for the two-modality layers), identical in exact arithmetic. */
+int vlm_regmean_rhs_diff(const float* w, const float* w_base, int out_f, int in_f, int64_t ldw,
+                         const void* g, int g_dtype, int64_t ldg, double alpha,
+                         double* acc, int64_t ldacc, int accumulate, void* stream);
+/* dst[rows][cols] (fp64) += src[rows][cols] (fp32): adds W_base back after the solve. */
+int vlm_widen_add(const float* src, int rows, int cols, int64_t lds, double* dst, int64_t ldd, void* stream);
 /* X = R * S^{-1} for SPD S (in_f x in_f, fp64, overwritten by its Cholesky factor); R (out_f x
  * in_f, fp64) is overwritten by X.  cuSOLVER potrf/potrs; off the hot path, timed separately.
  * Synchronises `stream` to read the factorisation status. */

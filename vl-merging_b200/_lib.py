@@ -84,6 +84,9 @@ SIGNATURES = {
     "vlm_gram_scale_accum": (c_int, [c_void_p, c_int, c_int, c_int64, c_double, c_void_p, c_int64, c_int, c_void_p]),
     "vlm_regmean_rhs": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_int, c_int64, c_double, c_void_p,
                                 c_int64, c_int, c_void_p]),
+    "vlm_regmean_rhs_diff": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_int, c_int64, c_double,
+                                     c_void_p, c_int64, c_int, c_void_p]),
+    "vlm_widen_add": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_int64, c_void_p]),
     "vlm_spd_solve_right": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p]),
     "vlm_sim_topk_splits": (c_int, [c_int64, c_int64]),
     "vlm_sim_topk": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int,

@@ -49,8 +49,9 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 
 template <typename GT>
 __global__ void __launch_bounds__(128)
-regmean_rhs_kernel(const float* __restrict__ w, int M, int K, int64_t ldw, const GT* __restrict__ g, int64_t ldg,
-                   double alpha, double oma, double* __restrict__ acc, int64_t ldacc, int accumulate) {
+regmean_rhs_kernel(const float* __restrict__ w, const float* __restrict__ w_sub, int M, int K, int64_t ldw,
+                   const GT* __restrict__ g, int64_t ldg, double alpha, double oma, double* __restrict__ acc,
+                   int64_t ldacc, int accumulate) {
   __shared__ double sa[2][BM][BKK + 1];  // W tile, widened
   __shared__ double sb[2][BKK][BN + 1];  // Ghat tile
   // blockIdx.x walks the rows of W (fast), blockIdx.y the columns of G: blocks that run together share one
@@ -65,7 +66,12 @@ regmean_rhs_kernel(const float* __restrict__ w, int M, int K, int64_t ldw, const
     for (int e = threadIdx.x; e < BM * BKK; e += 128) {
       const int r = e / BKK, kk = e % BKK;
       const int gm = m0 + r, gk = k0 + kk;
-      sa[buf][r][kk] = (gm < M && gk < K) ? (double)w[(int64_t)gm * ldw + gk] : 0.0;
+      double v = 0.0;
+      if (gm < M && gk < K) {
+        v = (double)w[(int64_t)gm * ldw + gk];
+        if (w_sub) v -= (double)w_sub[(int64_t)gm * ldw + gk];    // exact: both widen exactly, the difference rounds once
+      }
+      sa[buf][r][kk] = v;
     }
     for (int e = threadIdx.x; e < BKK * BN; e += 128) {
       const int kk = e / BN, cc = e % BN;
@@ -116,11 +122,12 @@ regmean_rhs_kernel(const float* __restrict__ w, int M, int K, int64_t ldw, const
 constexpr int TM = 128, TN = 128, TK = 32, TSTAGES = 3;
 constexpr int W_PITCH = TK + 4;  // floats: fragment reads hit 32 distinct banks
 
-template <typename GT>
+template <typename GT, bool SUB>
 struct RhsSmem {
   static constexpr int G_PITCH = TN + (sizeof(GT) == 4 ? 8 : 4);  // conflict-free k-major fragment reads
   float w[TSTAGES][TM][W_PITCH];
   GT g[TSTAGES][TK][G_PITCH];
+  float w_sub[SUB ? TSTAGES : 1][SUB ? TM : 1][SUB ? W_PITCH : 4];   // SUB: the tile of the subtracted weight
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
@@ -129,13 +136,14 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src,
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "r"(n) : "memory");
 }
 
-template <typename GT>
+// SUB: the left operand is W - W_sub (same pitch), formed in fp64 when a fragment is read.
+template <typename GT, bool SUB>
 __global__ void __launch_bounds__(512, 1)
-regmean_rhs_pipelined_kernel(const float* __restrict__ w, int M, int K, int64_t ldw, const GT* __restrict__ g,
-                             int64_t ldg, double alpha, double oma, double* __restrict__ acc, int64_t ldacc,
-                             int accumulate) {
+regmean_rhs_pipelined_kernel(const float* __restrict__ w, const float* __restrict__ w_sub, int M, int K, int64_t ldw,
+                             const GT* __restrict__ g, int64_t ldg, double alpha, double oma, double* __restrict__ acc,
+                             int64_t ldacc, int accumulate) {
   extern __shared__ __align__(16) uint8_t rhs_smem_raw[];
-  RhsSmem<GT>& sm = *reinterpret_cast<RhsSmem<GT>*>(rhs_smem_raw);
+  RhsSmem<GT, SUB>& sm = *reinterpret_cast<RhsSmem<GT, SUB>*>(rhs_smem_raw);
   constexpr int GV = 16 / sizeof(GT);  // G elements per 16-byte chunk
   const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;  // x walks W rows: co-running blocks share G strips
   const int N = K;
@@ -149,6 +157,8 @@ regmean_rhs_pipelined_kernel(const float* __restrict__ w, int M, int K, int64_t 
       const int r = e / (TK / 4), ch = e % (TK / 4);
       const bool ok = (m0 + r) < M && k0 < K;
       cp_async16(&sm.w[slot][r][ch * 4], w + (int64_t)(ok ? m0 + r : 0) * ldw + (ok ? k0 : 0) + ch * 4, ok);
+      if constexpr (SUB)
+        cp_async16(&sm.w_sub[slot][r][ch * 4], w_sub + (int64_t)(ok ? m0 + r : 0) * ldw + (ok ? k0 : 0) + ch * 4, ok);
     }
     constexpr int chunks_per_row = TN / GV;
     for (int e = tid; e < TK * chunks_per_row; e += 512) {  // G tile: 32 rows x 128 columns
@@ -173,7 +183,10 @@ regmean_rhs_pipelined_kernel(const float* __restrict__ w, int M, int K, int64_t 
     for (int ks = 0; ks < TK; ks += 4) {
       double a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = (double)sm.w[slot][wm + i * 8 + (lane >> 2)][ks + (lane & 3)];
+      for (int i = 0; i < 4; ++i) {
+        a[i] = (double)sm.w[slot][wm + i * 8 + (lane >> 2)][ks + (lane & 3)];
+        if constexpr (SUB) a[i] -= (double)sm.w_sub[slot][wm + i * 8 + (lane >> 2)][ks + (lane & 3)];
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int kk = ks + (lane & 3), nn = wn + j * 8 + (lane >> 2);
@@ -271,41 +284,87 @@ extern "C" int vlm_gram_scale_accum(const void* g, int g_dtype, int d, int64_t l
   return 0;
 }
 
-extern "C" int vlm_regmean_rhs(const float* w, int out_f, int in_f, int64_t ldw, const void* g, int g_dtype,
-                               int64_t ldg, double alpha, double* acc, int64_t ldacc, int accumulate, void* stream) {
+namespace vlm {
+namespace {
+template <typename GT, bool SUB>
+int launch_rhs_pipelined(const float* w, const float* w_sub, int out_f, int in_f, int64_t ldw, const void* g, int64_t ldg,
+                         double alpha, double* acc, int64_t ldacc, int accumulate, cudaStream_t s) {
+  dim3 grid((out_f + TM - 1) / TM, (in_f + TN - 1) / TN);
+  auto kernel = regmean_rhs_pipelined_kernel<GT, SUB>;
+  VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RhsSmem<GT, SUB>)));
+  kernel<<<grid, 512, sizeof(RhsSmem<GT, SUB>), s>>>(w, w_sub, out_f, in_f, ldw, static_cast<const GT*>(g), ldg, alpha,
+                                                     1.0 - alpha, acc, ldacc, accumulate);
+  return 0;
+}
+
+int regmean_rhs_impl(const char* who, const float* w, const float* w_sub, int out_f, int in_f, int64_t ldw, const void* g,
+                     int g_dtype, int64_t ldg, double alpha, double* acc, int64_t ldacc, int accumulate, void* stream) {
   VLM_REQUIRE(w && g && acc && out_f > 0 && in_f > 0 && ldw >= in_f && ldg >= in_f && ldacc >= in_f,
-              VLM_ERR_INVALID_ARG, "vlm_regmean_rhs: bad arguments");
-  VLM_REQUIRE(g_dtype == VLM_F64 || g_dtype == VLM_F32, VLM_ERR_INVALID_ARG,
-              "vlm_regmean_rhs: g_dtype must be VLM_F64 or VLM_F32");
+              VLM_ERR_INVALID_ARG, "%s: bad arguments", who);
+  VLM_REQUIRE(g_dtype == VLM_F64 || g_dtype == VLM_F32, VLM_ERR_INVALID_ARG, "%s: g_dtype must be VLM_F64 or VLM_F32", who);
   auto s = static_cast<cudaStream_t>(stream);
   const int gelem = g_dtype == VLM_F64 ? 8 : 4;
   const bool pipelined = in_f % TK == 0 && (ldw % 4) == 0 && ((ldg * gelem) % 16) == 0 && (ldacc % 2) == 0 &&
-                         (reinterpret_cast<uintptr_t>(w) % 16) == 0 && (reinterpret_cast<uintptr_t>(g) % 16) == 0 &&
-                         (reinterpret_cast<uintptr_t>(acc) % 16) == 0;
+                         (reinterpret_cast<uintptr_t>(w) % 16) == 0 && (reinterpret_cast<uintptr_t>(w_sub) % 16) == 0 &&
+                         (reinterpret_cast<uintptr_t>(g) % 16) == 0 && (reinterpret_cast<uintptr_t>(acc) % 16) == 0;
   if (pipelined) {
-    dim3 grid((out_f + TM - 1) / TM, (in_f + TN - 1) / TN);
-    if (g_dtype == VLM_F64) {
-      auto kernel = regmean_rhs_pipelined_kernel<double>;
-      VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RhsSmem<double>)));
-      kernel<<<grid, 512, sizeof(RhsSmem<double>), s>>>(w, out_f, in_f, ldw, static_cast<const double*>(g), ldg, alpha,
-                                                       1.0 - alpha, acc, ldacc, accumulate);
-    } else {
-      auto kernel = regmean_rhs_pipelined_kernel<float>;
-      VLM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RhsSmem<float>)));
-      kernel<<<grid, 512, sizeof(RhsSmem<float>), s>>>(w, out_f, in_f, ldw, static_cast<const float*>(g), ldg, alpha,
-                                                      1.0 - alpha, acc, ldacc, accumulate);
-    }
+    int rc;
+    if (g_dtype == VLM_F64)
+      rc = w_sub ? launch_rhs_pipelined<double, true>(w, w_sub, out_f, in_f, ldw, g, ldg, alpha, acc, ldacc, accumulate, s)
+                 : launch_rhs_pipelined<double, false>(w, w_sub, out_f, in_f, ldw, g, ldg, alpha, acc, ldacc, accumulate, s);
+    else
+      rc = w_sub ? launch_rhs_pipelined<float, true>(w, w_sub, out_f, in_f, ldw, g, ldg, alpha, acc, ldacc, accumulate, s)
+                 : launch_rhs_pipelined<float, false>(w, w_sub, out_f, in_f, ldw, g, ldg, alpha, acc, ldacc, accumulate, s);
+    if (rc) return rc;
     VLM_CUDA(cudaGetLastError());
     count_launch();
     return 0;
   }
   dim3 grid((out_f + BM - 1) / BM, (in_f + BN - 1) / BN);
   if (g_dtype == VLM_F64)
-    regmean_rhs_kernel<double><<<grid, 128, 0, s>>>(w, out_f, in_f, ldw, static_cast<const double*>(g), ldg, alpha,
+    regmean_rhs_kernel<double><<<grid, 128, 0, s>>>(w, w_sub, out_f, in_f, ldw, static_cast<const double*>(g), ldg, alpha,
                                                     1.0 - alpha, acc, ldacc, accumulate);
   else
-    regmean_rhs_kernel<float><<<grid, 128, 0, s>>>(w, out_f, in_f, ldw, static_cast<const float*>(g), ldg, alpha,
+    regmean_rhs_kernel<float><<<grid, 128, 0, s>>>(w, w_sub, out_f, in_f, ldw, static_cast<const float*>(g), ldg, alpha,
                                                    1.0 - alpha, acc, ldacc, accumulate);
+  VLM_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) widen_add_kernel(const float* __restrict__ src, int rows, int cols, int64_t lds,
+                                                        double* __restrict__ dst, int64_t ldd) {
+  const int64_t n = (int64_t)rows * cols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / cols, c = e - r * cols;
+    dst[r * ldd + c] = __dadd_rn(dst[r * ldd + c], (double)src[r * lds + c]);
+  }
+}
+}  // namespace
+}  // namespace vlm
+
+extern "C" int vlm_regmean_rhs(const float* w, int out_f, int in_f, int64_t ldw, const void* g, int g_dtype,
+                               int64_t ldg, double alpha, double* acc, int64_t ldacc, int accumulate, void* stream) {
+  return regmean_rhs_impl("vlm_regmean_rhs", w, nullptr, out_f, in_f, ldw, g, g_dtype, ldg, alpha, acc, ldacc, accumulate,
+                          stream);
+}
+
+extern "C" int vlm_regmean_rhs_diff(const float* w, const float* w_base, int out_f, int in_f, int64_t ldw, const void* g,
+                                    int g_dtype, int64_t ldg, double alpha, double* acc, int64_t ldacc, int accumulate,
+                                    void* stream) {
+  VLM_REQUIRE(w_base != nullptr, VLM_ERR_INVALID_ARG, "vlm_regmean_rhs_diff: w_base is NULL");
+  return regmean_rhs_impl("vlm_regmean_rhs_diff", w, w_base, out_f, in_f, ldw, g, g_dtype, ldg, alpha, acc, ldacc,
+                          accumulate, stream);
+}
+
+extern "C" int vlm_widen_add(const float* src, int rows, int cols, int64_t lds, double* dst, int64_t ldd, void* stream) {
+  VLM_REQUIRE(src && dst && rows > 0 && cols > 0 && lds >= cols && ldd >= cols, VLM_ERR_INVALID_ARG,
+              "vlm_widen_add: bad arguments");
+  int nsm = 0;
+  if (int rc = device_sm_count(&nsm)) return rc;
+  const int64_t n = (int64_t)rows * cols;
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)nsm * 8);
+  widen_add_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, rows, cols, lds, dst, ldd);
   VLM_CUDA(cudaGetLastError());
   count_launch();
   return 0;

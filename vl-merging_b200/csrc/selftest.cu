@@ -822,9 +822,30 @@ static void regmean_case(int out_f, int in_f, double alpha) {
       num += e * e;
     }
   const double solve_err = sqrt(num / den);
-  const bool ok = rhs_err < 1e-13 && sbad == 0 && solve_err < 1e-10;
-  printf("REGMEAN out=%d in=%d alpha=%.2f rhs_relF=%.2e scaleG_mismatch=%.0f solve_residual=%.2e  %s\n", out_f, in_f,
-         alpha, rhs_err, sbad, solve_err, ok ? "OK" : "FAIL");
+  // difference form: (W - W2) * Ghat through vlm_regmean_rhs_diff, then + W2 through vlm_widen_add
+  std::vector<float> W2(W.size());
+  for (auto& v : W2) v = frand();
+  float* dW2;
+  CK(cudaMalloc(&dW2, W2.size() * 4));
+  CK(cudaMemcpy(dW2, W2.data(), W2.size() * 4, cudaMemcpyHostToDevice));
+  VK(vlm_regmean_rhs_diff(dW, dW2, out_f, in_f, in_f, dG, VLM_F64, in_f, alpha, dR, in_f, 0, nullptr));
+  VK(vlm_widen_add(dW2, out_f, in_f, in_f, dR, in_f, nullptr));
+  CK(cudaMemcpy(X.data(), dR, R.size() * 8, cudaMemcpyDeviceToHost));
+  double dnum = 0, dden = 0;
+  for (int o = 0; o < out_f; ++o)
+    for (int c = 0; c < in_f; ++c) {
+      double acc = W2[(size_t)o * in_f + c];
+      for (int k = 0; k < in_f; ++k)
+        acc += ((double)W[(size_t)o * in_f + k] - (double)W2[(size_t)o * in_f + k]) * Gh[(size_t)k * in_f + c];
+      const double e = X[(size_t)o * in_f + c] - acc;
+      dnum += e * e;
+      dden += acc * acc;
+    }
+  const double diff_err = sqrt(dnum / dden);
+  CK(cudaFree(dW2));
+  const bool ok = rhs_err < 1e-13 && sbad == 0 && solve_err < 1e-10 && diff_err < 1e-13;
+  printf("REGMEAN out=%d in=%d alpha=%.2f rhs_relF=%.2e scaleG_mismatch=%.0f solve_residual=%.2e diff_form_relF=%.2e  %s\n",
+         out_f, in_f, alpha, rhs_err, sbad, solve_err, diff_err, ok ? "OK" : "FAIL");
   if (!ok) ++g_fail;
   CK(cudaFree(dG));
   CK(cudaFree(dS));
@@ -960,6 +981,7 @@ int main(int argc, char** argv) {
 
   regmean_case(96, 128, 1.0);
   regmean_case(200, 192, 0.9);
+  regmean_case(70, 100, 0.9);     // the 64 x 64 kernel (in_f not a multiple of 32)
 
   // SYRK: small shapes against a host fp64 Gram
   syrk_case<float>("f32 1 tile", VLM_F32, 64, 128, 0, true, 0, 2e-3);

@@ -386,20 +386,48 @@ def _regmean_linears(lib, state_dict, grams, lin_ops, mine, cost, alpha, device,
             operand(state_dict[wkey], False)
     info = torch.zeros(len(lin_ops), 2, dtype=torch.int32, device=device)
 
+    def base_weight(idx):
+        """With M >= 2 experts: (sum_m W_m Ghat_m) S^-1 = W_base + (sum_{m != base} (W_m - W_base) Ghat_m) S^-1 with
+        S = sum_m Ghat_m — one GEMM fewer than the formula as written (vilt_module.py:423-434), the same value in
+        exact arithmetic.  The base is the last expert, when all weights share one pitch."""
+        experts = lin_ops[idx].regmean
+        if len(experts) < 2:
+            return None
+        ws = [operand(state_dict[wkey], False) for wkey, _ in experts]
+        return ws[-1] if all(w.stride(0) == ws[-1].stride(0) for w in ws) else None
+
     def enqueue_rhs(idx, st):
         out_f, in_f = shapes[idx]
-        for n, (wkey, gkey) in enumerate(lin_ops[idx].regmean):
+        base = base_weight(idx)
+        experts = lin_ops[idx].regmean
+        first = True
+        for n, (wkey, gkey) in enumerate(experts):
             w, g = operand(state_dict[wkey], False), operand(grams[gkey], True)
             gdt = _lib.VLM_F64 if g.dtype == torch.float64 else _lib.VLM_F32
             _lib.check(lib.vlm_gram_scale_accum(g.data_ptr(), gdt, in_f, g.stride(0), alpha, summed[idx].data_ptr(),
                                                 summed[idx].stride(0), int(n > 0), st))
-            _lib.check(lib.vlm_regmean_rhs(w.data_ptr(), out_f, in_f, w.stride(0), g.data_ptr(), gdt, g.stride(0),
-                                           alpha, acc[idx].data_ptr(), acc[idx].stride(0), int(n > 0), st))
+            if base is None:
+                _lib.check(lib.vlm_regmean_rhs(w.data_ptr(), out_f, in_f, w.stride(0), g.data_ptr(), gdt, g.stride(0),
+                                               alpha, acc[idx].data_ptr(), acc[idx].stride(0), int(n > 0), st))
+            elif n < len(experts) - 1:
+                _lib.check(lib.vlm_regmean_rhs_diff(w.data_ptr(), base.data_ptr(), out_f, in_f, w.stride(0), g.data_ptr(),
+                                                    gdt, g.stride(0), alpha, acc[idx].data_ptr(), acc[idx].stride(0),
+                                                    int(not first), st))
+                first = False
+
+    def enqueue_finish(idx, st):
+        """After the solve: add W_base back (see base_weight)."""
+        base = base_weight(idx)
+        if base is not None:
+            out_f, in_f = shapes[idx]
+            _lib.check(lib.vlm_widen_add(base.data_ptr(), out_f, in_f, base.stride(0), acc[idx].data_ptr(),
+                                         acc[idx].stride(0), st))
 
     def enqueue_solve(idx, st):
         out_f, in_f = shapes[idx]
         _lib.check(lib.vlm_spd_solve_right_async(summed[idx].data_ptr(), in_f, summed[idx].stride(0), acc[idx].data_ptr(),
                                                  out_f, acc[idx].stride(0), info[idx].data_ptr(), st))
+        enqueue_finish(idx, st)
 
     order = sorted(mine, key=lambda i: (-cost(lin_ops[i]), i))
     n_streams = max(1, min(int(n_streams), len(mine)))
@@ -454,6 +482,7 @@ def _regmean_linears(lib, state_dict, grams, lin_ops, mine, cost, alpha, device,
                 if e.code == _lib.ERR_NOT_SPD:  # the reference's torch.inverse raises on a singular sum too
                     raise torch.linalg.LinAlgError(f"{lin_ops[idx].dst}: {e}") from e
                 raise
+            enqueue_finish(idx, cur.cuda_stream)
             if stats is not None:
                 stats["lu_fallbacks"] = stats.get("lu_fallbacks", 0) + 1
         elif potrs != 0:
