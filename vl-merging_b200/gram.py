@@ -3,14 +3,15 @@ src/cache_gram_matrices.py:236-281 and the artefact written at :349.
 
 Reference                                   here
 ------------------------------------------  ----------------------------------------------------------
-middle_representations = defaultdict(float)  GramCache (fp32 [d,d] device buffers, one per hooked module)
+middle_representations = defaultdict(float)  GramCache ([d,d] device buffers, one per hooked module: fp32, or fp64
+                                             in the RegMean-grade modes precision="int8x4" / "fp64")
 hook_gram_input(module, input, output)       GramCache.hook_gram_input — same signature, same use of
-                                             module.module_name; one vlm_syrk_accum launch on the
-                                             current stream instead of fp64 cast + DGEMM + .cpu()
+                                             module.module_name; one vlm_syrk_accum (/_i8x4 /_f64) launch on
+                                             the current stream instead of fp64 cast + DGEMM + .cpu()
 registration loop (:278-281)                 GramCache.register(model, use_moe)
 torch.save(middle_representations, path)     GramCache.save(path): {name: fp64 CPU (d,d)} — the file
                                              regmean() loads (vilt_module.py:386)
-(absent: every DDP rank writes its own sums) GramCache.all_reduce(): ONE NCCL all-reduce of the flat arena
+(absent: every DDP rank writes its own sums) GramCache.all_reduce(): ONE NCCL all-reduce of the packed upper triangles
 """
 from collections import defaultdict
 
@@ -106,7 +107,8 @@ def _reduce_counts(buffers, names, calls, rows, group):
 
 
 class GramCache:
-    """Accumulates G[name] += X^T X for every hooked module call, on the GPU, in fp32.
+    """Accumulates G[name] += X^T X for every hooked module call, on the GPU (fp32 Grams from one TF32 tensor-core pass by
+    default; exact fp64 Grams from the integer tensor cores or the fp64 pipe on request: `precision`).
 
     All buffers of the modules known at register() time live in one flat arena, so the data-parallel
     reduction is a single all-reduce and the buffers never move.  Modules whose width is only known

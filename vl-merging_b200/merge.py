@@ -4,7 +4,7 @@ regmean (:366-531).  Same names, same config keys, same key layout of the result
 (fp32, and fp64 for RegMean's linear weights); the arithmetic runs in libvlmerge:
 
   * every elementwise target of a call goes through ONE vlm_merge_plan launch (kernel (b));
-  * RegMean's W*Ghat / sum Ghat / solve run per linear through vlm_regmean_rhs,
+  * RegMean's W*Ghat / sum Ghat / solve run per linear through vlm_regmean_rhs(_diff),
     vlm_gram_scale_accum and vlm_spd_solve_right (kernel (c) + cuSOLVER).
 
 Inputs may live on the CPU (the reference's case: torch.load(map_location="cpu")) or already on the
@@ -339,8 +339,8 @@ def _workspace(device, numel):
 
 
 def _regmean_linears(lib, state_dict, grams, lin_ops, mine, cost, alpha, device, n_streams, results, stats=None):
-    """The linear problems `mine` of regmean(): per problem vlm_gram_scale_accum + vlm_regmean_rhs per expert, then
-    vlm_spd_solve_right_async, on n_streams CUDA streams (largest problem first, each to the least loaded stream;
+    """The linear problems `mine` of regmean(): per problem vlm_gram_scale_accum per expert + vlm_regmean_rhs_diff per
+    expert but the last (the difference form, see base_weight below), then vlm_spd_solve_right_async + vlm_widen_add, on n_streams CUDA streams (largest problem first, each to the least loaded stream;
     n_streams = 1: everything on the caller's stream, and `stats` receives the RHS / solve split from CUDA events).
     Every buffer is carved out BEFORE the streams fork — one fresh fp64 arena for the results (the returned tensors
     are views of it), one cached workspace for the summed Grams, operands staged on the caller's stream — so no
