@@ -96,6 +96,29 @@ def test_full_size_properties(dtype, d):
     assert err.item() < 1e-4      # 10x inside the BASELINE tolerance at calibration sizes, all dtypes
 
 
+@pytest.mark.parametrize("dtype,d", [(torch.float32, 768), (torch.float32, 3072), (torch.float16, 3072), (torch.float32, 4096)])
+def test_full_size_properties_int8x4(dtype, d):
+    """The exact integer-tensor-core mode at BASELINE sizes: symmetry, the trace identity and 256 sampled rows against
+    fp64 at 1e-8 (the RegMean-grade bar), and additivity over a split of the rows (each call picks its own column
+    exponents, so the two results agree to the quantisation error, not bit for bit)."""
+    rows = 36928
+    x = (_x((rows, d), torch.float32, 12, positive=(d >= 3072)).cuda() * torch.linspace(0.02, 25.0, d, device="cuda")).to(dtype)
+    cache = vlm.GramCache(precision="int8x4")
+    cache.accumulate("g", x.view(64, 577, d))
+    g = cache.gram("g")
+    assert g.dtype == torch.float64 and torch.equal(g, g.T)
+    xd = x.double()
+    trace = (xd * xd).sum().item()
+    assert abs(g.trace().item() - trace) / trace < 1e-9
+    idx = torch.arange(0, d, max(1, d // 256), device="cuda")[:256]
+    ref_rows = xd[:, idx].T @ xd
+    assert ((g[idx] - ref_rows).norm() / ref_rows.norm()).item() < 1e-8
+    halves = vlm.GramCache(precision="int8x4")
+    halves.accumulate("g", x[: 32 * 577].view(32, 577, d))
+    halves.accumulate("g", x[32 * 577:].view(32, 577, d))
+    assert ((halves.gram("g") - g).norm() / g.norm()).item() < 1e-8
+
+
 def test_registration_and_reference_file_format(tmp_path):
     cfg = vlm.vlmo_config("tiny")
     model = vlm.init_synthetic_(vlm.VLMo(cfg).eval(), seed=1).cuda()
