@@ -169,7 +169,9 @@ def run_ours(args):
     amp = {"fp32": None, "bf16": torch.bfloat16, "fp16": torch.float16}[args.autocast]
 
     TimedCache = make_timed_cache(vlm)
-    cache = TimedCache(dev, defer_bytes=args.defer_mb << 20, max_pending_bytes=args.defer_cap_mb << 20)
+    exact = args.gram_precision in ("int8x4", "fp64")      # RegMean-grade modes: fp64 Grams, launched from the hook
+    cache = TimedCache(dev, defer_bytes=0 if exact else args.defer_mb << 20, max_pending_bytes=args.defer_cap_mb << 20,
+                       precision=args.gram_precision)
     cache.register(model, use_moe=True)
     B = args.batch
     host_batches = [vlm.synthetic_batch(B, cfg, seed=1234 + rank * 16 + i) for i in range(2)]
@@ -305,14 +307,27 @@ def run_ours(args):
     # TF32 runs at half the bf16 tensor rate; the MEASURED bf16 figure (sustained: kernel timed inside a long step)
     peak_tf = peaks["bf16_tflops_sustained"] * (1.0 if sixteen else 0.5)
     achieved_tf = tot_flops / (tot_ms * 1e-3) * 1e-12 if tot_ms > 0 else 0.0
+    if args.gram_precision == "int8x4":
+        # 13 int8 digit-plane products per Gram at twice the bf16 tensor rate: the effective peak on the 1x flop count
+        peak_tf = peaks["bf16_tflops_sustained"] * 2.0 / 13.0
+        traffic = ncu_dram_traffic("r02_syrk_i8x4_36928x3072.summary.csv")
+    elif args.gram_precision == "fp64":
+        peak_tf, traffic = 40.0, None                      # B200 fp64 tensor peak (nominal)
+    elif args.gram_precision == "tf32x3":
+        peak_tf, traffic = peak_tf / 3.0, ncu_dram_traffic("r02_syrk_2sm_split_36928x3072.summary.csv")
     roofline = {
-        "kernel": "syrk_2sm_kernel (CTA pairs, one tcgen05.mma.cta_group::2 kind::tf32 stream per pair, TMA loads, TMEM accumulators, TMA reduce-add)" if not sixteen
-        else "syrk_2sm_kernel (mixed kind::tf32 / kind::f16 launches under autocast)",
+        "kernel": {"int8x4": "syrk_i8x4_kernel (fp32 -> four int8 digit planes; 13 tcgen05.mma.cta_group::2 kind::i8 products, int32 TMEM accumulators, fp64 TMA reduce-add) incl. its digit pre-pass",
+                   "fp64": "syrk_f64_kernel (DMMA m8n8k4, red.global.add.f64)",
+                   "tf32x3": "syrk_2sm_kernel, split mode (hi'hi + hi'lo + lo'hi) incl. vlm_tf32_split"}.get(args.gram_precision) or
+        ("syrk_2sm_kernel (CTA pairs, one tcgen05.mma.cta_group::2 kind::tf32 stream per pair, TMA loads, TMEM accumulators, TMA reduce-add)" if not sixteen
+         else "syrk_2sm_kernel (mixed kind::tf32 / kind::f16 launches under autocast)"),
         "bound": "tensor", "achieved": round(achieved_tf, 2), "peak": round(peak_tf, 1), "unit": "TFLOP/s",
         "frac": round(achieved_tf / peak_tf, 4), "traffic": traffic,
         "traffic_note": "dram read+write bytes of ONE 36928x3072 fp32 launch (ncu --set full, profiles/); its algorithmic minimum is one read of X = 453.8 MB",
-        "frac_of_nominal_1.1PF_tf32": round(achieved_tf / 1100.0, 4) if not sixteen else None,
-        "peak_source": f"{peaks['source']}: bf16_tflops_sustained{' / 2 (TF32)' if not sixteen else ''}",
+        "frac_of_nominal_1.1PF_tf32": round(achieved_tf / 1100.0, 4) if (not sixteen and args.gram_precision == "tf32") else None,
+        "peak_source": {"int8x4": f"{peaks['source']}: bf16_tflops_sustained x 2 (int8) / 13 products, on the 1x (symmetric) flop count",
+                        "fp64": "nominal B200 fp64 tensor peak", "tf32x3": f"{peaks['source']}: bf16_tflops_sustained / 2 / 3 products"}.get(
+                            args.gram_precision, f"{peaks['source']}: bf16_tflops_sustained{' / 2 (TF32)' if not sixteen else ''}"),
         "flops_per_launch_avg": tot_flops / n_ev, "ms_per_launch_avg": tot_ms / n_ev, "launches_timed": len(cache.events), "grams_accumulated": n_problems,
         "syrk_share_of_step": round(tot_ms / (ms if ms > 0 else 1), 4),
         "by_shape": {k: {"launches": v[0], "ms_avg": round(v[1] / v[0], 4), "tflops": round(v[2] / (v[1] * 1e-3) * 1e-12, 1)}
@@ -448,7 +463,7 @@ def run_ours(args):
         if world > 1:
             cache.all_reduce(group)
         regmean = bench_regmean(vlm, model, cfg, cache, dev, group, world, args)
-        if world == 1 and not args.no_gramfile:
+        if world == 1 and not args.no_gramfile and not exact:   # the packed container holds fp32 Grams
             gram_file = bench_gramfile(vlm, cache, dev)
         if world == 1 and args.model == "base":
             regmean.update(bench_regmean_chain(vlm, model, cfg, cache, dev, step, dev_batches, B))
@@ -503,7 +518,9 @@ def run_ours(args):
         out = {
             "metric": METRIC, "value": round(value, 2), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if not sixteen else args.autocast,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": ({"int8x4": "int8x4 (exact digit-plane products, fp64 Grams)", "fp64": "f64", "tf32x3": "tf32x3"}.get(args.gram_precision, "tf32")
+                      if not sixteen else f"{args.autocast}" + ("" if args.gram_precision == "tf32" else f" + {args.gram_precision} Grams")),
             "data": "synthetic (hash-seeded images U(-1,1) 384px + 40-token ids; random-init VLMo weights)",
             "config": {"workload": f"RegMean Gram caching, VLMo-{args.model} all_moe, {B} x (577 image + 40 text tokens) per GPU per step; "
                                    "96 Grams (72 x 768^2 + 24 x 3072^2)" if args.model == "base" else f"RegMean Gram caching, VLMo-{args.model} all_moe",
@@ -511,9 +528,10 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (each step streams >2 GB of weights and activations)",
                        "gram_hooks": (f"activations <= {args.defer_mb} MB are held by reference and issued as grouped launches "
                                       f"(flush at {args.defer_cap_mb} MB pending and after every forward); larger ones launch "
-                                      "from the hook") if args.defer_mb > 0 else "one SYRK launch per hook call",
+                                      "from the hook") if (args.defer_mb > 0 and not exact) else "one SYRK launch per hook call",
+                       "gram_precision": args.gram_precision,
                        "allreduce_ms_in_timed_region": round(ar_ms, 3), "allreduce_ms_after_barrier": ar_alone_ms,
-                       "allreduce": (f"packed upper triangles of the {n_live} live Grams in one NCCL all-reduce "
+                       "allreduce": (f"packed {'fp64' if exact else 'fp32'} upper triangles of the {n_live} live Grams in one NCCL all-reduce "
                                      f"({reduce_bytes / 1e6:.0f} MB)") if world > 1 else None},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "merge": merge, "reference_hook_on_gpu": ref_gpu, "regmean": regmean, "gram_file": gram_file, "fused_route": fused, "irtr": irtr, "vitl": vitl, "gram_parity_rel_fro": parity,
@@ -1162,6 +1180,8 @@ def main():
                     help="GramCache(defer_bytes=...): activations of at most this many MB (text tower, 768-wide image "
                          "activations) are grouped into shared launches; 0 = one launch per hook call")
     ap.add_argument("--defer-cap-mb", type=int, default=1024, help="flush grouped launches once this much is pending")
+    ap.add_argument("--gram-precision", default="tf32", choices=["tf32", "tf32x3", "int8x4", "fp64"],
+                    help="GramCache precision of the headline run (default: the single TF32 pass; int8x4 / fp64: RegMean-grade fp64 Grams)")
     ap.add_argument("--no-regmean", action="store_true")
     ap.add_argument("--no-gramfile", action="store_true", help="skip timing the Gram file formats (writes ~2.7 GB to a temp dir)")
     ap.add_argument("--fused", action="store_true",

@@ -225,7 +225,7 @@ class GramCache:
         self._finalized = False
         code = _DTYPES[keep.dtype]
         nbytes = rows * ldx * elem
-        if self.precision == "int8x4" and d % 128 == 0 and rows * d >= (1 << 21) \
+        if self.precision == "int8x4" and d % 128 == 0 and rows * d >= (1 << 20) \
                 and ptr % 16 == 0 and ldx % 4 == 0 and seg_stride % 4 == 0:
             nbytes = int(self._lib.vlm_syrk_i8x4_scratch_bytes(rows, d))
             scratch = self._plane_scratch((nbytes + 3) // 4)
