@@ -144,6 +144,17 @@ int vlm_sym_unpack(const float* packed, int d, void* out, int out_dtype, int64_t
 /* The same for fp64 Grams (the int8x4 / fp64 cache modes): packed fp64 upper triangle <-> full symmetric fp64. */
 int vlm_sym_pack_upper_f64(const double* g, int d, int64_t ldg, double* packed, void* stream);
 int vlm_sym_unpack_f64(const double* packed, int d, double* out, int64_t ldo, void* stream);
+/* All Grams of a cache in ONE launch: items[i] = {full (d x d, pitch ld), packed, d}; every item has the element type
+ * `dtype` (VLM_F32 or VLM_F64) on both sides.  pack reads `full`, unpack writes it (both triangles). */
+typedef struct vlm_sym_item {
+  const void* full;
+  void* packed;
+  int32_t d;
+  int32_t reserved;
+  int64_t ld;
+} vlm_sym_item;
+int vlm_sym_pack_upper_batch(const vlm_sym_item* items, int n, int dtype, void* stream);
+int vlm_sym_unpack_batch(const vlm_sym_item* items, int n, int dtype, void* stream);
 
 /* Host-only view of vlm_syrk_accum's work decomposition for (rows, d) on a device with nsm SMs
  * (elem_bytes 4 = f32, 2 = bf16/f16): writes segments as 5 int32 each {row_block_col0, col_block_col0,

@@ -37,6 +37,40 @@ def test_pack_unpack_bit_exact(d):
         assert (got[:, d:] == -1.0).all()
 
 
+@pytest.mark.parametrize("dtype,code", [(torch.float32, 0), (torch.float64, 3)])
+def test_batched_pack_unpack_bit_exact(dtype, code):
+    """vlm_sym_pack_upper_batch / vlm_sym_unpack_batch: Grams of mixed widths in one launch each (the exchange buffer of
+    GramCache.all_reduce and the packed Gram file), fp32 and fp64, padded leading dimensions."""
+    dims = [1, 31, 32, 33, 192, 768, 1000, 5, 256]
+    torch.manual_seed(7)
+    full = [torch.randn(d, d + (i % 3), dtype=dtype, device="cuda")[:, :d] for i, d in enumerate(dims)]
+    upper = [torch.triu(a) + torch.tril(torch.full_like(a, float("nan")), -1) for a in full]
+    upper = [torch.empty(d, d + (i % 3), dtype=dtype, device="cuda")[:, :d].copy_(u) for i, (d, u) in enumerate(zip(dims, upper))]
+    sizes = [d * (d + 1) // 2 for d in dims]
+    flat = torch.full((sum(sizes),), -7.0, dtype=dtype, device="cuda")
+    lib, stream = _lib.lib(), torch.cuda.current_stream().cuda_stream
+    esz = flat.element_size()
+    items = (_lib.SymItem * len(dims))()
+    off = 0
+    for it, u, d, sz in zip(items, upper, dims, sizes):
+        it.full, it.packed, it.d, it.ld = u.data_ptr(), flat.data_ptr() + esz * off, d, u.stride(0)
+        off += sz
+    _lib.check(lib.vlm_sym_pack_upper_batch(items, len(dims), code, stream))
+    got = flat.cpu().numpy()
+    off = 0
+    for a, d, sz in zip(full, dims, sizes):
+        assert np.array_equal(got[off: off + sz], a.cpu().numpy()[np.triu_indices(d)]), d
+        off += sz
+    outs = [torch.full((d, d + 2), -1.0, dtype=dtype, device="cuda") for d in dims]
+    for it, o in zip(items, outs):
+        it.full, it.ld = o.data_ptr(), o.stride(0)
+    _lib.check(lib.vlm_sym_unpack_batch(items, len(dims), code, stream))
+    for a, o, d in zip(full, outs, dims):
+        sym = (torch.triu(a) + torch.triu(a, 1).t()).cpu().numpy()
+        assert np.array_equal(o.cpu().numpy()[:, :d], sym) and (o.cpu().numpy()[:, d:] == -1.0).all(), d
+    assert lib.vlm_sym_pack_upper_batch(items, len(dims), 1, stream) == -1          # bf16 is not a Gram type
+
+
 def test_hand_written_file_loads(tmp_path):
     rng = np.random.default_rng(1)
     grams = {}

@@ -29,6 +29,11 @@ class MergeSeg(ctypes.Structure):
     ]
 
 
+class SymItem(ctypes.Structure):
+    """vlm_sym_item"""
+    _fields_ = [("full", c_void_p), ("packed", c_void_p), ("d", c_int32), ("reserved", c_int32), ("ld", c_int64)]
+
+
 class SyrkProblem(ctypes.Structure):
     """vlm_syrk_problem"""
     _fields_ = [
@@ -72,6 +77,8 @@ SIGNATURES = {
     "vlm_sym_unpack": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p]),
     "vlm_sym_pack_upper_f64": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "vlm_sym_unpack_f64": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p]),
+    "vlm_sym_pack_upper_batch": (c_int, [POINTER(SymItem), c_int, c_int, c_void_p]),
+    "vlm_sym_unpack_batch": (c_int, [POINTER(SymItem), c_int, c_int, c_void_p]),
     "vlm_syrk_schedule_host": (c_int, [c_int64, c_int, c_int, c_int, POINTER(c_int32), c_int, POINTER(c_int32),
                                        c_int, POINTER(c_int)]),
     "vlm_syrk_pair_schedule_host": (c_int, [c_int64, c_int, c_int, c_int, POINTER(c_int32), c_int, POINTER(c_int32),

@@ -366,9 +366,9 @@ class GramCache:
     def all_reduce(self, group=None, packed=True):
         """Data-parallel calibration: sum the per-rank Gram buffers (ONE NCCL all-reduce over NVLink).
         The reference has no such step (every DDP rank writes its own file).
-        packed: only the upper triangles of the Grams that fired travel — vlm_sym_pack_upper(_f64) into one flat
+        packed: only the upper triangles of the Grams that fired travel — vlm_sym_pack_upper_batch (one launch) into one flat
         buffer, one all-reduce of it (VLMo-base: 0.54 GB instead of the 1.17 GB arena with its lower triangles
-        and never-fired `vl` experts; twice that for the fp64 Grams of the int8x4 / fp64 modes), vlm_sym_unpack(_f64)
+        and never-fired `vl` experts; twice that for the fp64 Grams of the int8x4 / fp64 modes), vlm_sym_unpack_batch
         back into the full symmetric buffers (which leaves the cache finalized).  packed=False: one all-reduce of the
         whole arena."""
         import torch.distributed as dist
@@ -387,22 +387,16 @@ class GramCache:
         sizes = [self.buffers[n].shape[0] * (self.buffers[n].shape[0] + 1) // 2 for n in live]
         flat = torch.empty(sum(sizes), dtype=self.dtype, device=self.device)
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        items = (_lib.SymItem * len(live))()
         off = 0
-        for n, sz in zip(live, sizes):
+        for it, n, sz in zip(items, live, sizes):
             g = self.buffers[n]
-            pack = self._lib.vlm_sym_pack_upper_f64 if f64 else self._lib.vlm_sym_pack_upper
-            _lib.check(pack(g.data_ptr(), g.shape[0], g.stride(0), flat.data_ptr() + esz * off, stream))
+            it.full, it.packed, it.d, it.ld = g.data_ptr(), flat.data_ptr() + esz * off, g.shape[0], g.stride(0)
             off += sz
+        code = _lib.VLM_F64 if f64 else _lib.VLM_F32
+        _lib.check(self._lib.vlm_sym_pack_upper_batch(items, len(live), code, stream))       # one launch for all Grams
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        off = 0
-        for n, sz in zip(live, sizes):
-            g = self.buffers[n]
-            if f64:
-                _lib.check(self._lib.vlm_sym_unpack_f64(flat.data_ptr() + esz * off, g.shape[0], g.data_ptr(), g.stride(0), stream))
-            else:
-                _lib.check(self._lib.vlm_sym_unpack(flat.data_ptr() + esz * off, g.shape[0], g.data_ptr(), _lib.VLM_F32,
-                                                    g.stride(0), stream))
-            off += sz
+        _lib.check(self._lib.vlm_sym_unpack_batch(items, len(live), code, stream))
         self._finalized = True
         self.last_reduce_bytes = flat.numel() * esz
 

@@ -16,7 +16,7 @@ row-major UPPER TRIANGLE in fp32 (a quarter of the bytes) as one flat blob:
 `GramCache.save_packed` / `save_packed` write it (pack kernel on the device, ONE device->host copy),
 `load_packed` reads it back as fp32 device matrices for `regmean` (ONE host->device copy + unpack kernel),
 and `export_reference` / `import_reference` convert to and from the reference's own file, so either side
-can consume the other's artefact.  The packing kernels are vlm_sym_pack_upper / vlm_sym_unpack.
+can consume the other's artefact.  The packing kernels are vlm_sym_pack_upper(_batch) / vlm_sym_unpack(_batch).
 """
 import json
 import os
@@ -76,12 +76,14 @@ def save_packed(grams, path, rows=None, calls=None, device=None):
     with torch.cuda.device(device):
         packed = torch.empty(total, dtype=torch.float32, device=device)
         stream = torch.cuda.current_stream(device).cuda_stream
-        for e in entries:
+        items, keep = (_lib.SymItem * len(entries))(), []
+        for it, e in zip(items, entries):
             g = grams[e["name"]].detach().to(device=device, dtype=torch.float32)
             if g.stride(1) != 1:
                 g = g.contiguous()
-            _lib.check(lib.vlm_sym_pack_upper(g.data_ptr(), e["d"], g.stride(0),
-                                              packed.data_ptr() + 4 * e["offset"], stream))
+            keep.append(g)
+            it.full, it.packed, it.d, it.ld = g.data_ptr(), packed.data_ptr() + 4 * e["offset"], e["d"], g.stride(0)
+        _lib.check(lib.vlm_sym_pack_upper_batch(items, len(entries), _lib.VLM_F32, stream))   # one launch for all Grams
         host = torch.empty(total, dtype=torch.float32, pin_memory=True)
         host.copy_(packed, non_blocking=True)
         torch.cuda.current_stream(device).synchronize()
@@ -139,11 +141,16 @@ def load_packed(path, device=None, dtype=torch.float32):
         packed = host.to(device, non_blocking=True)
         stream = torch.cuda.current_stream(device).cuda_stream
         code = _lib.VLM_F32 if dtype == torch.float32 else _lib.VLM_F64
-        for e in entries:
-            g = torch.empty(e["d"], e["d"], dtype=dtype, device=device)
-            _lib.check(lib.vlm_sym_unpack(packed.data_ptr() + 4 * e["offset"], e["d"], g.data_ptr(), code,
-                                          g.stride(0), stream))
-            out[e["name"]] = g
+        items = (_lib.SymItem * len(entries))()
+        for it, e in zip(items, entries):
+            g = out[e["name"]] = torch.empty(e["d"], e["d"], dtype=dtype, device=device)
+            if dtype == torch.float32:       # same element type on both sides: one launch for all Grams
+                it.full, it.packed, it.d, it.ld = g.data_ptr(), packed.data_ptr() + 4 * e["offset"], e["d"], g.stride(0)
+            else:                            # widening to the reference's fp64: one launch per Gram
+                _lib.check(lib.vlm_sym_unpack(packed.data_ptr() + 4 * e["offset"], e["d"], g.data_ptr(), code,
+                                              g.stride(0), stream))
+        if dtype == torch.float32:
+            _lib.check(lib.vlm_sym_unpack_batch(items, len(entries), _lib.VLM_F32, stream))
         torch.cuda.current_stream(device).synchronize()   # `packed` and `host` may be released after this
     return out
 
