@@ -40,7 +40,7 @@ constexpr int kI8PlaneBytes = 32 * 128;   // 32 rows x 128 int8 columns
 constexpr int kI8Planes = 4;
 constexpr int kI8Phases = 3;              // {groups 4, 3}, {groups 2, 1}, {group 0}
 constexpr int kI8SlabBytes = 16384;         // 128 rows x 16 fp64 columns: one TMA reduce-add box
-constexpr int kI8SmemBytes = k2Stages * k2StageBytes + kI8SlabBytes + 1280 + 1024;   // stages, slab, barriers
+constexpr int kI8SmemBytes = k2Stages * k2StageBytes + 2 * kI8SlabBytes + 1280 + 1024;   // stages, two slabs, barriers
 
 struct I8Args {
   double* g;
@@ -97,7 +97,7 @@ syrk_i8x4_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
   uint8_t* slab = smem + kNS * kStageB;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(slab + kI8SlabBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slab + 2 * kI8SlabBytes);
   uint64_t* full = bars;                  // used in the leader only
   uint64_t* empty = bars + kNS;
   uint64_t* tfull = bars + 2 * kNS;
@@ -236,7 +236,7 @@ syrk_i8x4_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constan
       const int row = q * 32 + lane;
       uint32_t acc_phase = 0;
       const uint32_t tempty0 = mapa_rank(smem_u32(tempty), 0);
-      const uint32_t rbase = smem_u32(slab) + row * 128;
+      uint32_t slab_counter = 0;            // two slabs: the conversion of one overlaps the TMA engine's read of the other
       for (int s = seg_begin; s < seg_end; ++s) {
         const PairSeg seg = segs[s];
         const int sb_t = seg.sb & 0xFFFF, ph = seg.sb >> 16;
@@ -265,8 +265,10 @@ syrk_i8x4_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constan
             const long long c = two ? (long long)(int)w[j] * 128 + (int)v[j] : (long long)(int)v[j];
             val[j] *= __ll2double_rn(c);
           }
-          if (epi_tid == 0) bulk_wait_group_read<0>();   // the previous slab has left shared memory
+          uint8_t* buf = slab + (slab_counter & 1) * kI8SlabBytes;
+          if (epi_tid == 0) bulk_wait_group_read<1>();   // the slab issued two slabs ago has left shared memory
           named_bar_sync(1, 128);
+          const uint32_t rbase = smem_u32(buf) + row * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const uint32_t addr = rbase + ((uint32_t)(c ^ (row & 7)) << 4);
@@ -275,9 +277,10 @@ syrk_i8x4_kernel(const __grid_constant__ CUtensorMap tm_p0, const __grid_constan
           fence_proxy_async_smem();
           named_bar_sync(1, 128);
           if (epi_tid == 0) {
-            tma_reduce_add_2d(&tm_g, slab, c0, row0);
+            tma_reduce_add_2d(&tm_g, buf, c0, row0);
             bulk_commit_group();
           }
+          ++slab_counter;
         }
         tc_fence_before();
         __syncwarp();
