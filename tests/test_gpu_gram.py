@@ -119,6 +119,29 @@ def test_full_size_properties_int8x4(dtype, d):
     assert ((halves.gram("g") - g).norm() / g.norm()).item() < 1e-8
 
 
+@pytest.mark.parametrize("precision", ["int8x4", "fp64", "tf32"])
+def test_non_finite_activations_poison_their_row_and_column(precision):
+    """An Inf or a NaN in an activation (fp16 overflow under autocast) makes row and column c of the reference's Gram
+    non-finite (cache_gram_matrices.py:251-252).  Every mode must show it too — in particular the integer path, whose
+    fixed-point digits could silently turn it into a finite number — and leave the other entries finite and right."""
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(8192, 256, device="cuda", generator=gen)
+    x[17, 5] = float("inf")
+    x[4000, 130] = float("nan")
+    cache = vlm.GramCache(precision=precision)
+    cache.accumulate("g", x)
+    g = cache.gram("g").double()
+    bad = torch.zeros(256, dtype=torch.bool, device="cuda")
+    bad[[5, 130]] = True
+    mask = bad[:, None] | bad[None, :]
+    assert not torch.isfinite(g[mask]).any()
+    assert torch.isfinite(g[~mask]).all()
+    xd = x.double()
+    ref = xd.T @ xd
+    err = ((g[~mask] - ref[~mask]).norm() / ref[~mask].norm()).item()
+    assert err < {"int8x4": 1e-8, "fp64": 1e-12, "tf32": 1e-3}[precision], err
+
+
 def test_registration_and_reference_file_format(tmp_path):
     cfg = vlm.vlmo_config("tiny")
     model = vlm.init_synthetic_(vlm.VLMo(cfg).eval(), seed=1).cuda()

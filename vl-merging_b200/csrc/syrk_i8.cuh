@@ -80,8 +80,11 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, const v
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
-// 2^e as a double, from its exponent bits (|e| < 1022: column exponents come from fp32 maxima)
-__device__ __forceinline__ double i8_pow2(int e) { return __hiloint2double((1023 + e) << 20, 0); }
+// 2^e as a double, from its exponent bits (|e| < 1022: column exponents come from fp32 maxima); NaN for a poisoned
+// column (exponent kI8Poison, minus whatever the caller subtracted from it)
+__device__ __forceinline__ double i8_pow2(int e) {
+  return e < -(1 << 19) ? __longlong_as_double(0x7ff8000000000000ll) : __hiloint2double((1023 + e) << 20, 0);
+}
 
 // segs: PairSeg with the phase (0: groups 4 and 3, 1: groups 2 and 1, 2: group 0) in bits 16.. of sb; k in 32-row chunks
 // tm_g: G as a 2-D fp64 tensor, box 16 columns x 128 rows (the epilogue's TMA reduce-adds)
@@ -324,7 +327,13 @@ __global__ void __launch_bounds__(256) i8_colmax_kernel(const T* __restrict__ x,
                                                         unsigned* __restrict__ amax_bits) {
   const int cq = blockIdx.x * 32 + (threadIdx.x & 31);
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_slab, r1 = min(rows, r0 + rows_per_slab);
-  float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+  // maxima of the BIT PATTERNS of |x| (non-negative floats order like their bit patterns; Inf and NaN order above
+  // every finite value, where fmaxf would drop a NaN): a non-finite activation poisons its column (i8_exps_kernel)
+  unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+  auto upd = [&](const float4& v) {
+    m0 = max(m0, __float_as_uint(v.x) & 0x7fffffffu), m1 = max(m1, __float_as_uint(v.y) & 0x7fffffffu);
+    m2 = max(m2, __float_as_uint(v.z) & 0x7fffffffu), m3 = max(m3, __float_as_uint(v.w) & 0x7fffffffu);
+  };
   int64_t r = r0 + (threadIdx.x >> 5);
   for (; r + 24 < r1; r += 32) {
     float4 v[4];
@@ -332,34 +341,39 @@ __global__ void __launch_bounds__(256) i8_colmax_kernel(const T* __restrict__ x,
     for (int u = 0; u < 4; ++u)
       v[u] = i8_load4(i8_row_ptr(x, r + 8 * u, ldx, seg_rows, seg_stride), cq);
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      m0 = fmaxf(m0, fabsf(v[u].x)), m1 = fmaxf(m1, fabsf(v[u].y)), m2 = fmaxf(m2, fabsf(v[u].z)), m3 = fmaxf(m3, fabsf(v[u].w));
+    for (int u = 0; u < 4; ++u) upd(v[u]);
   }
-  for (; r < r1; r += 8) {
-    const float4 v = i8_load4(i8_row_ptr(x, r, ldx, seg_rows, seg_stride), cq);
-    m0 = fmaxf(m0, fabsf(v.x)), m1 = fmaxf(m1, fabsf(v.y)), m2 = fmaxf(m2, fabsf(v.z)), m3 = fmaxf(m3, fabsf(v.w));
-  }
+  for (; r < r1; r += 8) upd(i8_load4(i8_row_ptr(x, r, ldx, seg_rows, seg_stride), cq));
   // the block's 8 row groups are combined in shared memory first: one atomic per column per block (with one per
   // thread, ~1000 same-address atomics per column serialised in L2 and took longer than the pass over X)
-  __shared__ float4 red[8][32];
-  red[threadIdx.x >> 5][threadIdx.x & 31] = make_float4(m0, m1, m2, m3);
+  __shared__ uint4 red[8][32];
+  red[threadIdx.x >> 5][threadIdx.x & 31] = make_uint4(m0, m1, m2, m3);
   __syncthreads();
   if (threadIdx.x < 128) {
-    const float* col = reinterpret_cast<const float*>(&red[0][0]) + threadIdx.x;
-    float m = col[0];
+    const unsigned* col = reinterpret_cast<const unsigned*>(&red[0][0]) + threadIdx.x;
+    unsigned m = col[0];
 #pragma unroll
-    for (int w = 1; w < 8; ++w) m = fmaxf(m, col[w * 128]);
-    atomicMax(amax_bits + blockIdx.x * 128 + threadIdx.x, __float_as_uint(m));   // non-negative floats order like their bit patterns
+    for (int w = 1; w < 8; ++w) m = max(m, col[w * 128]);
+    atomicMax(amax_bits + blockIdx.x * 128 + threadIdx.x, m);
   }
 }
 
 // E_c with 2^E_c > max |x[:, c]| (clamped below so that 2^(26 - E_c) is a finite float), and that scale as a float,
-// written over the column maximum it was derived from
+// written over the column maximum it was derived from.  A column holding an Inf or a NaN gets the exponent kI8Poison:
+// its digits are zero and the epilogue turns its row and column of the Gram into NaN, as the reference's fp64 product
+// would (cache_gram_matrices.py:251-252) — never a finite number.
+constexpr int kI8Poison = -(1 << 20);
 __global__ void i8_exps_kernel(unsigned* __restrict__ amax_bits_then_scales, int d, int* __restrict__ exps) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= d) return;
-  const float m = __uint_as_float(amax_bits_then_scales[c]);
-  const int e = (m > 0.f && isfinite(m)) ? max(ilogbf(m) + 1, -100) : 0;
+  const unsigned bits = amax_bits_then_scales[c];
+  if (bits >= 0x7f800000u) {              // Inf or NaN somewhere in the column
+    exps[c] = kI8Poison;
+    amax_bits_then_scales[c] = 0;         // scale 0: the digits of the whole column are zero
+    return;
+  }
+  const float m = __uint_as_float(bits);
+  const int e = m > 0.f ? max(ilogbf(m) + 1, -100) : 0;
   exps[c] = e;
   amax_bits_then_scales[c] = (unsigned)(127 + 26 - e) << 23;   // the float 2^(26 - e)
 }
