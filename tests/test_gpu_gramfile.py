@@ -145,3 +145,36 @@ def test_conversion_to_and_from_the_reference_file(calibrated, tmp_path):
     again = gramfile.load_packed(tmp_path / "again.vlmgram", dtype=torch.float64)
     for k, w in want.items():
         assert torch.equal(again[k].cpu(), w)
+
+
+def test_fp64_container_keeps_the_regmean_grade_grams_exactly(tmp_path):
+    """A RegMean-grade cache (fp64 Gram buffers) writes the container in fp64 — half the reference file, every value
+    kept — and regmean from that file equals regmean on the live cache; narrowing on load and the fp64 import of the
+    reference's own file work too."""
+    cfg = vlm.vlmo_config("tiny")
+    model = vlm.init_synthetic_(vlm.VLMo(cfg).eval(), seed=1).cuda()
+    cache = vlm.GramCache(precision="int8x4")
+    cache.register(model, use_moe=True)
+    with torch.no_grad():
+        for seed in (5, 6, 7):
+            model(vlm.synthetic_batch(8, cfg, seed=seed, device="cuda"))
+    cache.remove_hooks()
+    nbytes = cache.save_packed(tmp_path / "g64.vlmgram")
+    cache.save(tmp_path / "g.pth")
+    assert 0.49 < nbytes / os.path.getsize(tmp_path / "g.pth") < 0.52
+    entries, _, fdtype = gramfile.read_header(tmp_path / "g64.vlmgram", with_dtype=True)
+    assert fdtype == torch.float64 and [e["name"] for e in entries] == cache.live_names()
+    want = cache.state_dict()
+    got = gramfile.load_packed(tmp_path / "g64.vlmgram")
+    got32 = gramfile.load_packed(tmp_path / "g64.vlmgram", dtype=torch.float32)
+    for k, w in want.items():
+        assert got[k].dtype == torch.float64 and torch.equal(got[k].cpu(), w)
+        assert got32[k].dtype == torch.float32 and torch.equal(got32[k].cpu(), w.float())
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    mcfg = dict(vlffn_start_layer_index=10, loss_names={"irtr": 1, "vqa": 0, "nlvr2": 0}, scaling_for_non_diag=0.9)
+    live = vlm.regmean(sd, mcfg, gram_matrices=cache)
+    packed = vlm.regmean(sd, dict(mcfg, gram_matrices=str(tmp_path / "g64.vlmgram")))
+    assert all(torch.equal(live[k], packed[k]) for k in live)
+    gramfile.import_reference(tmp_path / "g.pth", tmp_path / "again64.vlmgram", dtype=torch.float64)
+    again = gramfile.load_packed(tmp_path / "again64.vlmgram")
+    assert all(torch.equal(again[k].cpu(), w) for k, w in want.items())

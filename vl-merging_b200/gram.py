@@ -445,11 +445,10 @@ class GramCache:
         torch.save(self.state_dict(), path)
 
     def save_packed(self, path):
-        """The packed fp32 upper-triangle container (gramfile.py): a quarter of the reference file's bytes;
-        regmean reads either format.  Returns the number of bytes written."""
+        """The packed upper-triangle container (gramfile.py) in the cache's own element type: fp32 (a quarter of the
+        reference file's bytes) or, for the RegMean-grade caches, fp64 (half); regmean reads either, and the
+        reference's own format.  Returns the number of bytes written."""
         from . import gramfile
-        if self.dtype == torch.float64:
-            raise RuntimeError("the packed container holds fp32 values: write fp64 Grams with save() (the reference's format)")
         return gramfile.save_packed(self, path)
 
     def reset(self):

@@ -8,13 +8,16 @@ row-major UPPER TRIANGLE in fp32 (a quarter of the bytes) as one flat blob:
 
     bytes 0..7     magic  b"VLMGRAM1"
     bytes 8..15    little-endian uint64: length H of the JSON header
-    bytes 16..16+H header: {"version": 1, "dtype": "float32", "layout": "upper_rowmajor",
+    bytes 16..16+H header: {"version": 1, "dtype": "float32" | "float64", "layout": "upper_rowmajor",
                             "entries": [{"name", "d", "offset" (in elements), "rows", "calls"}, ...]}
     zero padding to a multiple of 4096
-    fp32 data: for each entry d*(d+1)/2 values, row r = columns r..d-1
+    data: for each entry d*(d+1)/2 values, row r = columns r..d-1
+
+dtype float32 is what the default cache accumulates; float64 (half the reference file instead of a quarter) keeps the
+Grams of the RegMean-grade caches (GramCache(precision="int8x4" / "fp64")) exactly.
 
 `GramCache.save_packed` / `save_packed` write it (pack kernel on the device, ONE device->host copy),
-`load_packed` reads it back as fp32 device matrices for `regmean` (ONE host->device copy + unpack kernel),
+`load_packed` reads it back as device matrices for `regmean` (ONE host->device copy + ONE unpack launch),
 and `export_reference` / `import_reference` convert to and from the reference's own file, so either side
 can consume the other's artefact.  The packing kernels are vlm_sym_pack_upper(_batch) / vlm_sym_unpack(_batch).
 """
@@ -53,16 +56,23 @@ def _device_of(device):
     return device
 
 
-def save_packed(grams, path, rows=None, calls=None, device=None):
+def save_packed(grams, path, rows=None, calls=None, device=None, dtype=None):
     """grams: {name: (d, d) tensor} (any float dtype / device; only the upper triangles are read) or a
-    GramCache.  Returns the number of bytes written."""
+    GramCache.  dtype: torch.float32 or torch.float64 of the stored values; None = float64 for a cache that
+    accumulates fp64 Grams, float32 otherwise.  Returns the number of bytes written."""
     if hasattr(grams, "buffers") and hasattr(grams, "live_names"):
+        if dtype is None:
+            dtype = grams.dtype
         cache = grams
         cache.flush()
         device = cache.device
         rows, calls = cache.rows, cache.calls
         grams = {n: cache.buffers[n] for n in cache.live_names()}
     device = _device_of(device)
+    dtype = dtype or torch.float32
+    if dtype not in (torch.float32, torch.float64):
+        raise ValueError("dtype must be torch.float32 or torch.float64")
+    esz, code = (4, _lib.VLM_F32) if dtype == torch.float32 else (8, _lib.VLM_F64)
     lib = _lib.lib()
     names = list(grams.keys())
     entries, total = [], 0
@@ -74,20 +84,21 @@ def save_packed(grams, path, rows=None, calls=None, device=None):
                         "calls": int((calls or {}).get(n, 0))})
         total += _packed_len(d)
     with torch.cuda.device(device):
-        packed = torch.empty(total, dtype=torch.float32, device=device)
+        packed = torch.empty(total, dtype=dtype, device=device)
         stream = torch.cuda.current_stream(device).cuda_stream
         items, keep = (_lib.SymItem * len(entries))(), []
         for it, e in zip(items, entries):
-            g = grams[e["name"]].detach().to(device=device, dtype=torch.float32)
+            g = grams[e["name"]].detach().to(device=device, dtype=dtype)
             if g.stride(1) != 1:
                 g = g.contiguous()
             keep.append(g)
-            it.full, it.packed, it.d, it.ld = g.data_ptr(), packed.data_ptr() + 4 * e["offset"], e["d"], g.stride(0)
-        _lib.check(lib.vlm_sym_pack_upper_batch(items, len(entries), _lib.VLM_F32, stream))   # one launch for all Grams
-        host = torch.empty(total, dtype=torch.float32, pin_memory=True)
+            it.full, it.packed, it.d, it.ld = g.data_ptr(), packed.data_ptr() + esz * e["offset"], e["d"], g.stride(0)
+        _lib.check(lib.vlm_sym_pack_upper_batch(items, len(entries), code, stream))   # one launch for all Grams
+        host = torch.empty(total, dtype=dtype, pin_memory=True)
         host.copy_(packed, non_blocking=True)
         torch.cuda.current_stream(device).synchronize()
-    header = json.dumps({"version": 1, "dtype": "float32", "layout": "upper_rowmajor", "entries": entries}).encode()
+    header = json.dumps({"version": 1, "dtype": "float32" if dtype == torch.float32 else "float64", "layout": "upper_rowmajor",
+                         "entries": entries}).encode()
     pre = MAGIC + struct.pack("<Q", len(header)) + header
     pad = (-len(pre)) % _ALIGN
     tmp = f"{path}.tmp.{os.getpid()}"
@@ -99,39 +110,45 @@ def save_packed(grams, path, rows=None, calls=None, device=None):
     finally:
         if os.path.exists(tmp):
             os.remove(tmp)
-    return len(pre) + pad + 4 * total
+    return len(pre) + pad + esz * total
 
 
-def read_header(path):
-    """(entries, data_offset_in_bytes) of a packed Gram file."""
+def read_header(path, with_dtype=False):
+    """(entries, data_offset_in_bytes) of a packed Gram file; with_dtype: (entries, offset, torch dtype of the values)."""
     with open(path, "rb") as f:
         if f.read(len(MAGIC)) != MAGIC:
             raise ValueError(f"{path} is not a packed Gram file (bad magic)")
         (hlen,) = struct.unpack("<Q", f.read(8))
         header = json.loads(f.read(hlen).decode())
-    if header.get("version") != 1 or header.get("layout") != "upper_rowmajor" or header.get("dtype") != "float32":
-        raise ValueError(f"{path}: unsupported packed Gram header {header.get('version')}/{header.get('layout')}")
+    if header.get("version") != 1 or header.get("layout") != "upper_rowmajor" or header.get("dtype") not in ("float32", "float64"):
+        raise ValueError(f"{path}: unsupported packed Gram header {header.get('version')}/{header.get('layout')}/{header.get('dtype')}")
     pre = len(MAGIC) + 8 + hlen
-    return header["entries"], pre + ((-pre) % _ALIGN)
+    off = pre + ((-pre) % _ALIGN)
+    if with_dtype:
+        return header["entries"], off, torch.float32 if header["dtype"] == "float32" else torch.float64
+    return header["entries"], off
 
 
-def load_packed(path, device=None, dtype=torch.float32):
-    """{name: full symmetric (d, d) device tensor} (fp32, or fp64 = the reference's dtype): what
-    regmean(gram_matrices=...) takes.  One host->device copy of the blob, one unpack launch per Gram."""
+def load_packed(path, device=None, dtype=None):
+    """{name: full symmetric (d, d) device tensor}: what regmean(gram_matrices=...) takes.  dtype: torch.float32 or
+    torch.float64 of the returned matrices; None = the file's own.  One host->device copy of the blob, then one unpack
+    launch for all Grams (one per Gram when an fp32 file is widened to fp64)."""
     device = _device_of(device)
+    entries, off, fdtype = read_header(path, with_dtype=True)
+    dtype = dtype or fdtype
     if dtype not in (torch.float32, torch.float64):
         raise ValueError("dtype must be torch.float32 or torch.float64")
-    entries, off = read_header(path)
+    esz = 4 if fdtype == torch.float32 else 8
     total = sum(_packed_len(e["d"]) for e in entries)
     size = os.path.getsize(path)
-    if size < off + 4 * total:
-        raise ValueError(f"{path}: truncated ({size} bytes, header promises {off + 4 * total})")
+    if size < off + esz * total:
+        raise ValueError(f"{path}: truncated ({size} bytes, header promises {off + esz * total})")
     lib = _lib.lib()
-    host = torch.empty(total, dtype=torch.float32, pin_memory=True)
+    host = torch.empty(total, dtype=fdtype, pin_memory=True)
     view, got = memoryview(host.numpy()).cast("B"), 0
     with open(path, "rb", buffering=0) as f:
         f.seek(off)
-        while got < 4 * total:           # one read() moves at most 2 GB
+        while got < esz * total:           # one read() moves at most 2 GB
             n = f.readinto(view[got:got + (1 << 30)])
             if not n:
                 raise ValueError(f"{path}: short read")
@@ -140,17 +157,20 @@ def load_packed(path, device=None, dtype=torch.float32):
     with torch.cuda.device(device):
         packed = host.to(device, non_blocking=True)
         stream = torch.cuda.current_stream(device).cuda_stream
-        code = _lib.VLM_F32 if dtype == torch.float32 else _lib.VLM_F64
+        same = dtype == fdtype or fdtype == torch.float64    # fp64 file: unpacked as fp64 (and narrowed after, if asked)
         items = (_lib.SymItem * len(entries))()
         for it, e in zip(items, entries):
-            g = out[e["name"]] = torch.empty(e["d"], e["d"], dtype=dtype, device=device)
-            if dtype == torch.float32:       # same element type on both sides: one launch for all Grams
-                it.full, it.packed, it.d, it.ld = g.data_ptr(), packed.data_ptr() + 4 * e["offset"], e["d"], g.stride(0)
-            else:                            # widening to the reference's fp64: one launch per Gram
-                _lib.check(lib.vlm_sym_unpack(packed.data_ptr() + 4 * e["offset"], e["d"], g.data_ptr(), code,
+            g = out[e["name"]] = torch.empty(e["d"], e["d"], dtype=fdtype if same else dtype, device=device)
+            if same:                         # same element type on both sides: one launch for all Grams
+                it.full, it.packed, it.d, it.ld = g.data_ptr(), packed.data_ptr() + esz * e["offset"], e["d"], g.stride(0)
+            else:                            # fp32 file widened to the reference's fp64: one launch per Gram
+                _lib.check(lib.vlm_sym_unpack(packed.data_ptr() + 4 * e["offset"], e["d"], g.data_ptr(), _lib.VLM_F64,
                                               g.stride(0), stream))
-        if dtype == torch.float32:
-            _lib.check(lib.vlm_sym_unpack_batch(items, len(entries), _lib.VLM_F32, stream))
+        if same:
+            _lib.check(lib.vlm_sym_unpack_batch(items, len(entries), _lib.VLM_F32 if fdtype == torch.float32 else _lib.VLM_F64,
+                                                stream))
+            if dtype != fdtype:
+                out = {k: v.to(dtype) for k, v in out.items()}
         torch.cuda.current_stream(device).synchronize()   # `packed` and `host` may be released after this
     return out
 
@@ -166,12 +186,13 @@ def export_reference(packed_path, reference_path, device=None):
     return reference_path
 
 
-def import_reference(reference_path, packed_path, device=None):
-    """The reference's Gram file -> packed container (values rounded to fp32; the lower triangles are dropped)."""
+def import_reference(reference_path, packed_path, device=None, dtype=torch.float32):
+    """The reference's Gram file -> packed container (the lower triangles are dropped; values rounded to fp32 unless
+    dtype=torch.float64)."""
     grams = torch.load(reference_path, map_location="cpu", weights_only=False)
-    return save_packed({k: v for k, v in grams.items() if torch.is_tensor(v)}, packed_path, device=device)
+    return save_packed({k: v for k, v in grams.items() if torch.is_tensor(v)}, packed_path, device=device, dtype=dtype)
 
 
-def packed_bytes(dims):
+def packed_bytes(dims, dtype=torch.float32):
     """Size of the data section for Grams of the given widths; e.g. VLMo-base IRTR: 72 x 768 + 24 x 3072."""
-    return 4 * int(np.sum([_packed_len(int(d)) for d in dims]))
+    return (4 if dtype == torch.float32 else 8) * int(np.sum([_packed_len(int(d)) for d in dims]))
