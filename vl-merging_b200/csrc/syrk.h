@@ -35,9 +35,10 @@ int syrk_tc_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, f
 struct PairSeg {
   int32_t sa, sb, k0, k1;
 };
-// seg_cap: chunks per accumulation (0: the default 128, or $VLM_SYRK_SEG_CHUNKS)
+// seg_cap: chunks per accumulation (0: the default 128, or $VLM_SYRK_SEG_CHUNKS); min_piece: shortest K piece a
+// left-over tile is cut into (0: 64 chunks for long sweeps, 8 for short ones)
 void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairSeg>* segs, std::vector<int>* off,
-                         int64_t seg_cap = 0);
+                         int64_t seg_cap = 0, int64_t min_piece = 0);
 // exact Gram on the integer tensor cores (syrk_i8.cuh): fp32 activations -> four int8 digit planes -> fp64 Gram
 size_t syrk_i8x4_scratch_bytes(int64_t rows, int d);
 int syrk_i8x4_launch(const void* x, int dtype, int64_t rows, int d, int64_t ldx, int64_t seg_rows, int64_t seg_stride, void* scratch,

@@ -217,7 +217,7 @@ PairKernel pick_kernel(int dtype) {
 // look-ahead prefetch (cp.async.bulk.prefetch.tensor) cost 8 %, half-height stages x 8 cost 14 %.  (Numbers of the
 // multicast pair kernel of round 1; the cta_group::2 kernel keeps the schedule unchanged.)
 void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairSeg>* segs, std::vector<int>* off,
-                         int64_t seg_cap_arg) {
+                         int64_t seg_cap_arg, int64_t min_piece_arg) {
   // chunks per accumulation: 4096 fp32 rows / 8192 16-bit rows.  Measured on the B200 with all-positive
   // activations 36928 x 3072: cap 128 / 256 / 512 / none -> rel. error 7.6e-4 / 7.8e-4 / 8.2e-4 / 1.0e-3 (fp32),
   // 2.2e-5 / 5.0e-5 / 8.8e-5 (bf16), at 742 / 753 / 766 / 779 TFLOP/s.
@@ -253,7 +253,11 @@ void build_pair_schedule(int64_t kc, int d, int nclusters_max, std::vector<PairS
   const int64_t rem = ntile - rounds * C;
   if (rem > 0) {
     const int64_t p_lo = std::max<int64_t>(1, (kc + seg_cap - 1) / seg_cap);
-    const int64_t p_hi = std::max<int64_t>(p_lo, kc / (kc >= 8 * 64 ? 64 : min_chunks));
+    // shortest K piece: 64 chunks for long sweeps, min_chunks for short ones when the problem runs alone (it has to
+    // fill the GPU by itself); a grouped launch with plenty of other work asks for 64 throughout (min_piece_arg), so
+    // that a 2560-row Gram is not cut into 8-chunk pieces whose 128 KB epilogues take longer than their mainloops
+    const int64_t min_piece = min_piece_arg > 0 ? min_piece_arg : (kc >= 8 * 64 ? 64 : min_chunks);
+    const int64_t p_hi = std::max<int64_t>(p_lo, kc / min_piece);
     int64_t best_p = p_lo;
     double best = 1e30;
     for (int64_t p = p_lo; p <= p_hi; ++p) {
@@ -582,6 +586,15 @@ int syrk_pair_batch_launch(const vlm_syrk_problem* probs, int n, int dtype, cuda
     std::vector<std::pair<int64_t, int>> shares;
   };
   std::map<std::pair<int64_t, int>, ShapeSched> by_shape;
+  // total work of the batch in (tile, chunk) units: with at least ~8 pieces of 64 chunks per cluster there is no need
+  // to cut short K ranges finely (ncu of the text group, 36 x [2560, 768] + 12 x [2560, 3072]: tensor pipe 72 % of
+  // elapsed with 8-chunk pieces — 2,640 segments whose epilogues outlast their mainloops)
+  int64_t batch_work = 0;
+  for (int p = 0; p < n; ++p) {
+    const int64_t nsb = (probs[p].d + 255) / 256;
+    batch_work += nsb * (nsb + 1) / 2 * ((probs[p].rows + bk - 1) / bk);
+  }
+  const int64_t min_piece = batch_work >= (int64_t)8 * 64 * C ? 64 : 0;
   for (int p = 0; p < n; ++p) {
     const vlm_syrk_problem& q = probs[p];
     if (int rc = check_alignment(q.x, elem, q.rows, q.ldx, q.g, q.ldg)) return rc;
@@ -594,7 +607,7 @@ int syrk_pair_batch_launch(const vlm_syrk_problem* probs, int n, int dtype, cuda
     auto found = by_shape.find({kc, q.d});
     if (found == by_shape.end()) {
       ShapeSched ss;
-      build_pair_schedule(kc, q.d, C, &ss.segs, &ss.off);
+      build_pair_schedule(kc, q.d, C, &ss.segs, &ss.off, 0, min_piece);
       for (int c = 0; c + 1 < (int)ss.off.size(); ++c) {
         int64_t cost = 0;
         for (int s = ss.off[c]; s < ss.off[c + 1]; ++s) cost += ss.segs[s].k1 - ss.segs[s].k0;
