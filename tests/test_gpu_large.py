@@ -66,17 +66,18 @@ def test_vitl_modality_arithmetic_bit_exact_vs_oracle(large_sd):
         assert np.array_equal(got[k].cpu().numpy(), want[k]), k
 
 
-def test_vitl_width_regmean_chain_4096(large_sd):
+@pytest.mark.parametrize("precision", ["fp64", "int8x4"])
+def test_vitl_width_regmean_chain_4096(large_sd, precision):
     """One ViT-L layer's four linear problems — (3072,1024), (1024,1024), (4096,1024), (1024,4096): the 4096-wide
     potrf / potrs and the 1024 / 4096 RHS shapes — with Grams cached on the device in fp64 mode from synthetic
     activations (post-GELU-like for fc2), against the oracle fed with numpy fp64 Grams of the same activations.
-    BASELINE.json: RegMean 1e-4."""
+    Both RegMean-grade Gram modes (fp64 DMMA; the integer tensor cores at 1024 / 4096 columns).  BASELINE.json: RegMean 1e-4."""
     cfg, sd = large_sd
     layer = 22                                       # has v, l AND vl experts; IRTR uses v and l (vilt_module.py:399-400)
     sub = {k: v for k, v in sd.items() if "transformer.blocks." not in k or f".blocks.{layer}." in k}
     sub = {k.replace(f".blocks.{layer}.", ".blocks.0."): v for k, v in sub.items()}
     gen = torch.Generator(device="cuda").manual_seed(3)
-    cache = vlm.GramCache(precision="fp64")
+    cache = vlm.GramCache(precision=precision)
     np_grams = {}
     for m, rows in (("v", 9232), ("l", 5120)):
         for name, d, positive in ((f"attn.{m}", 1024, False), (f"attn.{m}.proj", 1024, False),
