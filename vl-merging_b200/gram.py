@@ -54,13 +54,29 @@ def select_hooked_modules(model, use_moe=True, all_keys=None):
             if any(name.endswith(k) for k in keys) and ".bias" not in name]
 
 
-def agree_on_buffers(buffers, group=None, make=None):
+def agree_on_buffers(buffers, group=None, make=None, device=None):
     """Ranks may hold different sets of lazily created buffers (a module whose width was unknown at register() fires on
     some ranks only): agree on the union of (name, width) first and create zero buffers for the names missing
-    locally, so every rank issues the same collectives on the same shapes.  Raises if two ranks disagree on a width."""
+    locally, so every rank issues the same collectives on the same shapes.  Raises if two ranks disagree on a width.
+    The common case — every rank holds the same set — costs one 16-byte all-reduce of a digest (max of the digest and
+    of its complement agree only if all digests are equal); only a mismatch pays for the all_gather_object."""
+    import hashlib
+
     import torch.distributed as dist
 
     mine = sorted((n, int(g.shape[0])) for n, g in buffers.items())
+    if device is None:
+        device = next(iter(buffers.values())).device if buffers else torch.device("cpu")
+    if dist.get_backend(group) == "nccl" and torch.device(device).type != "cuda":
+        device = torch.device("cuda", torch.cuda.current_device())
+    elif dist.get_backend(group) != "nccl":
+        device = torch.device("cpu")
+    digest = int.from_bytes(hashlib.sha256(repr(mine).encode()).digest()[:7], "little")      # 56 bits: exact in int64
+    t = torch.tensor([digest, -digest], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)    # every rank takes part, with or without buffers
+    hi, neg_lo = t.tolist()
+    if hi == -neg_lo:                                         # max == min: the same set everywhere (same test on every rank)
+        return [n for n, _ in mine]
     everyone = [None] * dist.get_world_size(group)
     dist.all_gather_object(everyone, mine, group=group)
     union = {}
@@ -378,7 +394,7 @@ class GramCache:
         if not packed:
             return reduce_gram_buffers(self.buffers, self._arenas, self.calls, self.rows, group)
         names = agree_on_buffers(self.buffers, group,
-                                 lambda d: torch.zeros(d, d, dtype=self.dtype, device=self.device))
+                                 lambda d: torch.zeros(d, d, dtype=self.dtype, device=self.device), device=self.device)
         _reduce_counts(self.buffers, names, self.calls, self.rows, group)    # after this, live_names() agrees on every rank
         live = [n for n in names if self.calls[n] > 0]
         if not live:
