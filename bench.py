@@ -171,7 +171,7 @@ def run_ours(args):
     TimedCache = make_timed_cache(vlm)
     exact = args.gram_precision in ("int8x4", "fp64")      # RegMean-grade modes: fp64 Grams, launched from the hook
     cache = TimedCache(dev, defer_bytes=0 if exact else args.defer_mb << 20, max_pending_bytes=args.defer_cap_mb << 20,
-                       precision=args.gram_precision)
+                       precision=args.gram_precision, symmetric=bool(args.symmetric and world > 1))
     cache.register(model, use_moe=True)
     B = args.batch
     host_batches = [vlm.synthetic_batch(B, cfg, seed=1234 + rank * 16 + i) for i in range(2)]
@@ -531,7 +531,9 @@ def run_ours(args):
                                       "from the hook") if (args.defer_mb > 0 and not exact) else "one SYRK launch per hook call",
                        "gram_precision": args.gram_precision,
                        "allreduce_ms_in_timed_region": round(ar_ms, 3), "allreduce_ms_after_barrier": ar_alone_ms,
-                       "allreduce": (f"packed {'fp64' if exact else 'fp32'} upper triangles of the {n_live} live Grams in one NCCL all-reduce "
+                       "allreduce": (f"ONE kernel over NVSwitch multicast memory (multimem.ld_reduce / multimem.st on the symmetric Gram arenas, "
+                                     f"{reduce_bytes / 1e6:.0f} MB of upper triangles, no staging buffer, no NCCL call)") if (world > 1 and cache.symmetric) else
+                                    (f"packed {'fp64' if exact else 'fp32'} upper triangles of the {n_live} live Grams in one NCCL all-reduce "
                                      f"({reduce_bytes / 1e6:.0f} MB)") if world > 1 else None},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "merge": merge, "reference_hook_on_gpu": ref_gpu, "regmean": regmean, "gram_file": gram_file, "fused_route": fused, "irtr": irtr, "vitl": vitl, "gram_parity_rel_fro": parity,
@@ -1182,6 +1184,8 @@ def main():
     ap.add_argument("--defer-cap-mb", type=int, default=1024, help="flush grouped launches once this much is pending")
     ap.add_argument("--gram-precision", default="tf32", choices=["tf32", "tf32x3", "int8x4", "fp64"],
                     help="GramCache precision of the headline run (default: the single TF32 pass; int8x4 / fp64: RegMean-grade fp64 Grams)")
+    ap.add_argument("--symmetric", action="store_true",
+                    help="N > 1: Gram arenas in torch symmetric memory, exchange as one multimem kernel instead of NCCL")
     ap.add_argument("--no-regmean", action="store_true")
     ap.add_argument("--no-gramfile", action="store_true", help="skip timing the Gram file formats (writes ~2.7 GB to a temp dir)")
     ap.add_argument("--fused", action="store_true",

@@ -156,6 +156,26 @@ typedef struct vlm_sym_item {
 int vlm_sym_pack_upper_batch(const vlm_sym_item* items, int n, int dtype, void* stream);
 int vlm_sym_unpack_batch(const vlm_sym_item* items, int n, int dtype, void* stream);
 
+/* The exchange step of data-parallel Gram caching as ONE kernel over NVSwitch multicast memory (the reference has no
+ * reduction: every DDP rank overwrites the same file, src/cache_gram_matrices.py:349).  multicast_base: the multicast
+ * mapping of a symmetric allocation that holds, at the same offsets on every rank, the Grams described by `spans`.
+ * The upper-triangular 32 x 32 tiles are dealt round-robin to the ranks; the owner reads a tile with
+ * multimem.ld_reduce.add (the switch returns the sum over all ranks) and multimem.st's it into every rank's copy:
+ * pack + all-reduce + unpack in one launch, bit-identical on all ranks; the lower triangles follow locally
+ * (vlm_sym_mirror_batch).  The caller
+ * brackets the launch with cross-rank barriers on `stream` (all ranks' accumulation before, all stores landed
+ * after).  fp32 Grams need d and ld multiples of 4; offsets 16-byte aligned. */
+typedef struct vlm_sym_span {
+  uint64_t offset_bytes;
+  int32_t d;
+  int32_t reserved;
+  int64_t ld;
+} vlm_sym_span;
+int vlm_sym_allreduce_multimem(void* multicast_base, const vlm_sym_span* spans, int n, int dtype, int rank, int world,
+                               void* stream);
+/* Local, in place, one launch: the lower triangle of every Gram in `spans` (offsets from `base`) from its upper one. */
+int vlm_sym_mirror_batch(void* base, const vlm_sym_span* spans, int n, int dtype, void* stream);
+
 /* Host-only view of vlm_syrk_accum's work decomposition for (rows, d) on a device with nsm SMs
  * (elem_bytes 4 = f32, 2 = bf16/f16): writes segments as 5 int32 each {row_block_col0, col_block_col0,
  * width_in_128_blocks, chunk_begin, chunk_end} and ncta+1 offsets into them.  Returns the number of

@@ -32,12 +32,31 @@ def _worker(rank, world, port, ret):
         cache.register(model)
         cache8 = vlm.GramCache(precision="int8x4")       # fp64 Gram buffers: the packed fp64 exchange
         cache8.register(model)
+        # the same exchange as ONE kernel over NVSwitch multicast memory (symmetric arenas), fp32 and fp64
+        cache_mc = vlm.GramCache(symmetric=True)
+        cache_mc.register(model)
+        cache_mc8 = vlm.GramCache(precision="fp64", symmetric=True)
+        cache_mc8.register(model)
         with torch.no_grad():
             model(vlm.synthetic_batch(2, cfg, seed=50 + rank, device="cuda"))   # this rank's shard of the calibration set
         cache.all_reduce()
         cache8.all_reduce()
         grams = cache.state_dict()
         grams8 = cache8.state_dict()
+        mc = {}
+        try:
+            cache_mc.all_reduce()
+            cache_mc8.all_reduce()
+            gm, gm8 = cache_mc.state_dict(), cache_mc8.state_dict()
+            mc = {"err32": max(((gm[k] - grams[k]).norm() / grams[k].norm()).item() for k in grams),
+                  "err64": max(((gm8[k] - grams8[k]).norm() / grams8[k].norm()).item() for k in grams8),
+                  "sym": all(torch.equal(gm[k], gm[k].T) and torch.equal(gm8[k], gm8[k].T) for k in grams),
+                  "pick32": gm["transformer.blocks.7.mlp.l.fc2"].numpy(), "pick64": gm8["transformer.blocks.0.attn.v"].numpy(),
+                  "calls": dict(cache_mc.calls) == dict(cache.calls), "n": len(gm)}
+        except RuntimeError as e:
+            if "multicast" not in str(e):
+                raise
+            mc = {"unsupported": str(e)}
         sd = {k: v.detach() for k, v in model.state_dict().items()}
         mcfg = dict(vlffn_start_layer_index=10, only_activate_used_experts=False, merge_ratio=0.5, sum_lambda=0.75,
                     scaling_for_non_diag=0.9, loss_names={"irtr": 1.0, "vqa": 0, "nlvr2": 0})
@@ -55,6 +74,7 @@ def _worker(rank, world, port, ret):
             "grams": {k: grams[k].numpy() for k in ("transformer.blocks.0.attn.v", "transformer.blocks.7.mlp.l.fc2")},
             "grams8": {k: grams8[k].numpy() for k in ("transformer.blocks.0.attn.v", "transformer.blocks.7.mlp.l.fc2")},
             "reduce_bytes": (cache.last_reduce_bytes, cache8.last_reduce_bytes),
+            "mc": mc,
             "n_grams": len(grams),
             "merged": {k: merged[k].cpu().numpy() for k in pick},
             "regmean": {k: rm[k].cpu().numpy() for k in pick},
@@ -90,6 +110,10 @@ def test_two_rank_calibration_and_sharded_merge():
     for k, g in r0["grams"].items():
         assert np.array_equal(g, r1["grams"][k])
         assert np.linalg.norm(g - want[k].numpy()) <= 1e-5 * np.linalg.norm(want[k].numpy())
+    if "unsupported" not in r0["mc"]:                       # the multimem exchange: same sums, bit-identical on both ranks
+        assert r0["mc"]["n"] == 96 and r0["mc"]["calls"] and r0["mc"]["sym"] and r1["mc"]["sym"]
+        assert max(r0["mc"]["err32"], r1["mc"]["err32"]) < 1e-6 and max(r0["mc"]["err64"], r1["mc"]["err64"]) < 1e-14
+        assert np.array_equal(r0["mc"]["pick32"], r1["mc"]["pick32"]) and np.array_equal(r0["mc"]["pick64"], r1["mc"]["pick64"])
     for k, g in r0["grams8"].items():                       # the RegMean-grade cache: packed fp64 upper triangles travel
         assert np.array_equal(g, r1["grams8"][k]) and np.array_equal(g, g.T)
         assert np.linalg.norm(g - want8[k].numpy()) <= 1e-13 * np.linalg.norm(want8[k].numpy())

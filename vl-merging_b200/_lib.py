@@ -34,6 +34,11 @@ class SymItem(ctypes.Structure):
     _fields_ = [("full", c_void_p), ("packed", c_void_p), ("d", c_int32), ("reserved", c_int32), ("ld", c_int64)]
 
 
+class SymSpan(ctypes.Structure):
+    """vlm_sym_span"""
+    _fields_ = [("offset_bytes", ctypes.c_uint64), ("d", c_int32), ("reserved", c_int32), ("ld", c_int64)]
+
+
 class SyrkProblem(ctypes.Structure):
     """vlm_syrk_problem"""
     _fields_ = [
@@ -79,6 +84,8 @@ SIGNATURES = {
     "vlm_sym_unpack_f64": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p]),
     "vlm_sym_pack_upper_batch": (c_int, [POINTER(SymItem), c_int, c_int, c_void_p]),
     "vlm_sym_unpack_batch": (c_int, [POINTER(SymItem), c_int, c_int, c_void_p]),
+    "vlm_sym_allreduce_multimem": (c_int, [c_void_p, POINTER(SymSpan), c_int, c_int, c_int, c_int, c_void_p]),
+    "vlm_sym_mirror_batch": (c_int, [c_void_p, POINTER(SymSpan), c_int, c_int, c_void_p]),
     "vlm_syrk_schedule_host": (c_int, [c_int64, c_int, c_int, c_int, POINTER(c_int32), c_int, POINTER(c_int32),
                                        c_int, POINTER(c_int)]),
     "vlm_syrk_pair_schedule_host": (c_int, [c_int64, c_int, c_int, c_int, POINTER(c_int32), c_int, POINTER(c_int32),

@@ -132,7 +132,7 @@ class GramCache:
     """
 
     def __init__(self, device=None, use_simt=False, defer_bytes=0, max_pending=256, max_pending_bytes=1 << 30,
-                 side_stream=False, precision="tf32"):
+                 side_stream=False, precision="tf32", symmetric=False):
         """precision: how fp32 activations reach the tensor cores.  "tf32" (default): one TF32 pass, operands rounded
         by TMA — Gram within ~3e-5 of the reference's fp64 Gram (cache_gram_matrices.py:251-252), inside the 1e-3
         tolerance, but its 2^-11 operand rounding noise is amplified by the inverse in regmean
@@ -159,6 +159,10 @@ class GramCache:
         every held activation and raises if one was written to.  The default 0 keeps the reference's immediate
         semantics.  Deferred activations stay allocated until the flush; a flush is forced
         after max_pending activations or max_pending_bytes of them.
+        symmetric=True (under an initialised torch.distributed NCCL group, one process per GPU of one NVSwitch domain):
+        the Gram arena is allocated in torch symmetric memory, and all_reduce() then runs as ONE kernel over the
+        NVSwitch multicast mapping (vlm_sym_allreduce_multimem: multimem.ld_reduce / multimem.st, no staging buffer,
+        no NCCL call) instead of pack -> NCCL all-reduce -> unpack.
         side_stream=True: the SYRK launches go to a second CUDA stream (ordered after the producer of each
         activation by an event), so they overlap the rest of the forward — its LayerNorm / GELU / softmax
         phases leave the tensor pipes idle; flush() joins the two streams.  Like deferral it holds a reference to
@@ -187,6 +191,7 @@ class GramCache:
         self.defer_bytes, self.max_pending, self.max_pending_bytes = int(defer_bytes), int(max_pending), int(max_pending_bytes)
         self._pending = []     # (dtype code, keep-alive tensor, g, ptr, rows, d, ldx, seg_rows, seg_stride)
         self._pending_bytes = 0
+        self.symmetric, self._symm = bool(symmetric), None   # symmetric-memory arena and its rendezvous handle
         self._side = torch.cuda.Stream(self.device) if side_stream else None
         self._side_keep = []   # activations a side-stream launch may still be reading
 
@@ -362,7 +367,16 @@ class GramCache:
         if not named_dims:
             return
         total = sum(d * d for _, d in named_dims)
-        arena = torch.zeros(total, dtype=self.dtype, device=self.device)
+        if self.symmetric:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            if self._arenas:
+                raise RuntimeError("GramCache(symmetric=True): register the model once (one symmetric arena)")
+            with torch.cuda.device(self.device):
+                arena = symm_mem.empty(total, dtype=self.dtype, device=self.device)
+            arena.zero_()
+        else:
+            arena = torch.zeros(total, dtype=self.dtype, device=self.device)
         off = 0
         for name, d in named_dims:
             self.buffers[name] = arena[off: off + d * d].view(d, d)
@@ -391,6 +405,8 @@ class GramCache:
         import torch.distributed as dist
 
         self.flush()
+        if self.symmetric and packed:
+            return self._all_reduce_multimem(group)
         if not packed:
             return reduce_gram_buffers(self.buffers, self._arenas, self.calls, self.rows, group)
         names = agree_on_buffers(self.buffers, group,
@@ -416,6 +432,49 @@ class GramCache:
         _lib.check(self._lib.vlm_sym_unpack_batch(items, len(live), code, stream))
         self._finalized = True
         self.last_reduce_bytes = flat.numel() * esz
+
+    def _all_reduce_multimem(self, group=None):
+        """all_reduce() of a symmetric cache: one kernel over the NVSwitch multicast mapping of the arena, bracketed by
+        two cross-rank barriers on the current stream.  Every rank ends with bit-identical, fully symmetric Grams."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = group if group is not None else dist.group.WORLD
+        names = agree_on_buffers(self.buffers, group,
+                                 lambda d: torch.zeros(d, d, dtype=self.dtype, device=self.device), device=self.device)
+        _reduce_counts(self.buffers, names, self.calls, self.rows, group)
+        live = [n for n in names if self.calls[n] > 0]
+        if not live:
+            return
+        if len(self._arenas) != 1:
+            raise RuntimeError("GramCache(symmetric=True): no symmetric arena (register() the model before calibrating)")
+        arena = self._arenas[0]
+        lo, hi = arena.data_ptr(), arena.data_ptr() + arena.numel() * arena.element_size()
+        if any(not (lo <= self.buffers[n].data_ptr() < hi) for n in live):
+            raise RuntimeError("GramCache(symmetric=True): a Gram buffer lives outside the symmetric arena (a module whose "
+                               "width was unknown at register()); use a plain cache (NCCL exchange) for this model")
+        if self._symm is None:
+            self._symm = symm_mem.rendezvous(arena, group)          # collective: every rank, same order
+        h = self._symm
+        mc = int(h.multicast_ptr or 0)
+        if mc == 0:
+            raise RuntimeError("GramCache(symmetric=True): this system offers no multicast mapping (NVSwitch + driver "
+                               "support needed); use a plain cache (NCCL exchange)")
+        spans = (_lib.SymSpan * len(live))()
+        for sp, n in zip(spans, live):
+            g = self.buffers[n]
+            sp.offset_bytes, sp.d, sp.ld = g.data_ptr() - lo, g.shape[0], g.stride(0)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        code = _lib.VLM_F64 if self.dtype == torch.float64 else _lib.VLM_F32
+        with torch.cuda.device(self.device):
+            h.barrier(channel=0)               # every rank's Gram launches have completed
+            _lib.check(self._lib.vlm_sym_allreduce_multimem(mc, spans, len(live), code, dist.get_rank(group),
+                                                            dist.get_world_size(group), stream))
+            h.barrier(channel=0)               # every rank's stores have landed everywhere
+            _lib.check(self._lib.vlm_sym_mirror_batch(lo, spans, len(live), code, stream))     # lower triangles, locally
+        self._finalized = True
+        esz = 8 if self.dtype == torch.float64 else 4
+        self.last_reduce_bytes = sum(self.buffers[n].shape[0] * (self.buffers[n].shape[0] + 1) // 2 for n in live) * esz
 
     def finalize(self):
         """Mirror the upper triangles into the lower ones (after the last accumulate / all_reduce)."""
