@@ -46,6 +46,24 @@ int device_sm_count(int* out) {
   return 0;
 }
 
+// The small descriptor tables of the batched launches come from cudaMallocAsync.  With its default release threshold
+// (0) the pool hands its memory back to the driver at every synchronisation and the next call pays a real allocation
+// (~0.3 ms, measured around the pack / unpack launches of GramCache.all_reduce): keep the pool's memory instead.
+int keep_async_pool() {
+  static bool done[64] = {};
+  int dev = 0;
+  VLM_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (dev >= 0 && dev < 64 && !done[dev]) {
+    cudaMemPool_t pool;
+    VLM_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t threshold = UINT64_MAX;
+    VLM_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    done[dev] = true;
+  }
+  return 0;
+}
+
 int require_sm100() {
   int nsm = 0, dev = 0;
   if (int rc = device_sm_count(&nsm)) return rc;

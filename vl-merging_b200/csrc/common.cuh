@@ -36,6 +36,7 @@ inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_o
 
 int device_sm_count(int* out);
 int require_sm100();
+int keep_async_pool();   // before cudaMallocAsync: do not return the pool's memory to the driver at every sync
 
 // ---- device-side PTX wrappers -----------------------------------------------------------------
 #ifdef __CUDACC__

@@ -163,6 +163,7 @@ int sym_batch(const vlm_sym_item* items, int n, int dtype, bool pack, cudaStream
     bands += (items[i].d + 31) / 32;
   }
   SymItemDev* dev = nullptr;
+  if (int rc = keep_async_pool()) return rc;
   VLM_CUDA(cudaMallocAsync(&dev, sizeof(SymItemDev) * n, s));
   VLM_CUDA(cudaMemcpyAsync(dev, host.data(), sizeof(SymItemDev) * n, cudaMemcpyHostToDevice, s));   // pageable: staged before return
   if (pack) {

@@ -142,6 +142,7 @@ int upload_spans(const vlm_sym_span* spans, int n, int dtype, const char* who, c
     host[i] = {spans[i].offset_bytes, spans[i].d, (int)*bands, spans[i].ld};
     *bands += nt;
   }
+  if (int rc = keep_async_pool()) return rc;
   VLM_CUDA(cudaMallocAsync(dev, sizeof(SpanDev) * n, s));
   VLM_CUDA(cudaMemcpyAsync(*dev, host.data(), sizeof(SpanDev) * n, cudaMemcpyHostToDevice, s));   // pageable: staged before return
   return 0;
