@@ -140,3 +140,24 @@ def _mismatch_job(rank, world):
 def test_width_mismatch_between_ranks_raises_instead_of_hanging():
     res = _spawn(_mismatch_job)
     assert all("width" in (res[r] or "") for r in range(2)), res
+
+
+def _empty_rank_job(rank, world):
+    """One rank saw no hooked module at all: it still takes part in the digest exchange and ends up with zero buffers
+    for the other rank's names (no rank skips a collective)."""
+    from collections import defaultdict
+
+    buffers = {} if rank == 0 else {"a": torch.full((3, 3), 2.0), "b": torch.full((2, 2), 5.0)}
+    calls = defaultdict(int, {} if rank == 0 else {"a": 1, "b": 2})
+    rows = defaultdict(int, {} if rank == 0 else {"a": 4, "b": 6})
+    reduce_gram_buffers(buffers, [], calls, rows, None)
+    return {k: v.numpy().copy() for k, v in buffers.items()}, dict(calls), dict(rows)
+
+
+def test_a_rank_without_buffers_takes_part_in_the_exchange():
+    res = _spawn(_empty_rank_job)
+    for rank in range(2):
+        bufs, calls, rows = res[rank]
+        assert sorted(bufs) == ["a", "b"]
+        assert np.array_equal(bufs["a"], np.full((3, 3), 2.0, np.float32)) and np.array_equal(bufs["b"], np.full((2, 2), 5.0, np.float32))
+        assert calls == {"a": 1, "b": 2} and rows == {"a": 4, "b": 6}
